@@ -1,0 +1,22 @@
+// core.cu — ABI version, thread-local error string, launch counter.
+#include <stdarg.h>
+#include <string.h>
+#include "common.cuh"
+
+namespace b2ctr {
+static thread_local char g_err[512] = "";
+std::atomic<long long> g_launches{0};
+void set_error(const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+}
+}  // namespace b2ctr
+
+extern "C" {
+int32_t b2ctr_abi_version(void) { return 1; }
+const char* b2ctr_last_error(void) { return b2ctr::g_err; }
+int64_t b2ctr_launch_count(void) { return (int64_t)b2ctr::g_launches.load(); }
+void b2ctr_reset_launch_count(void) { b2ctr::g_launches.store(0); }
+}

@@ -1,0 +1,214 @@
+// gemm_simt.cu — exact-fp32 GEMM on the FFMA pipe with fused bias/activation epilogue.
+//
+// This is the B2CTR_GEMM_FP32 precision mode: bit-for-bit fp32 products and fp32 accumulation,
+// used for parity runs and as the checker of the tcgen05 split-bf16 path (gemm_tc.cu).
+// Replaces tf.tensordot/tf.matmul of deepctr/layers/core.py:193-195 (DNN), deepctr/layers/core.py:106
+// (LocalActivationUnit), deepctr/layers/interaction.py:414-418 (CrossNet), :754-757 (InteractingLayer).
+#include "common.cuh"
+
+namespace b2ctr {
+
+constexpr int kBK = 8;
+constexpr int kThreads = 256;
+
+struct GemmArgs {
+  const float* a; const float* b; float* c; const float* bias; float* ws;
+  int64_t m, n, k;
+  int64_t sam, sak;  // A(m,k) = a[m*sam + k*sak]
+  int64_t sbk, sbn;  // B(k,n) = b[k*sbk + n*sbn]
+  int64_t ldc;
+  int64_t k_per_split;
+  float alpha;
+  int act, accumulate, splits;
+};
+
+template <int BM, int BN, bool A_KCONTIG, bool B_NCONTIG>
+__global__ void __launch_bounds__(kThreads) sgemm_kernel(const GemmArgs g) {
+  constexpr int TM = BM / 16, TN = BN / 16;
+  constexpr int APT = BM * kBK / kThreads, BPT = BN * kBK / kThreads;
+  constexpr int PAD = 4;
+  __shared__ __align__(16) float As[2][kBK][BM + PAD];
+  __shared__ __align__(16) float Bs[2][kBK][BN + PAD];
+
+  const int t = threadIdx.x;
+  const int tx = t % 16, ty = t / 16;
+  const int64_t m0 = (int64_t)blockIdx.y * BM, n0 = (int64_t)blockIdx.x * BN;
+  const int64_t kbeg = (int64_t)blockIdx.z * g.k_per_split;
+  const int64_t kend = kbeg + g.k_per_split < g.k ? kbeg + g.k_per_split : g.k;
+
+  float acc[TM][TN];
+#pragma unroll
+  for (int i = 0; i < TM; ++i)
+#pragma unroll
+    for (int j = 0; j < TN; ++j) acc[i][j] = 0.f;
+
+  float ra[APT], rb[BPT];
+  auto load_tile = [&](int64_t k0) {
+#pragma unroll
+    for (int i = 0; i < APT; ++i) {
+      const int l = t + i * kThreads;
+      const int kk = A_KCONTIG ? l % kBK : l / BM;
+      const int mm = A_KCONTIG ? l / kBK : l % BM;
+      const int64_t gm = m0 + mm, gk = k0 + kk;
+      ra[i] = (gm < g.m && gk < kend) ? g.a[gm * g.sam + gk * g.sak] : 0.f;
+    }
+#pragma unroll
+    for (int i = 0; i < BPT; ++i) {
+      const int l = t + i * kThreads;
+      const int kk = B_NCONTIG ? l / BN : l % kBK;
+      const int nn = B_NCONTIG ? l % BN : l / kBK;
+      const int64_t gn = n0 + nn, gk = k0 + kk;
+      rb[i] = (gn < g.n && gk < kend) ? g.b[gk * g.sbk + gn * g.sbn] : 0.f;
+    }
+  };
+  auto store_tile = [&](int buf) {
+#pragma unroll
+    for (int i = 0; i < APT; ++i) {
+      const int l = t + i * kThreads;
+      const int kk = A_KCONTIG ? l % kBK : l / BM;
+      const int mm = A_KCONTIG ? l / kBK : l % BM;
+      As[buf][kk][mm] = ra[i];
+    }
+#pragma unroll
+    for (int i = 0; i < BPT; ++i) {
+      const int l = t + i * kThreads;
+      const int kk = B_NCONTIG ? l / BN : l % kBK;
+      const int nn = B_NCONTIG ? l % BN : l / kBK;
+      Bs[buf][kk][nn] = rb[i];
+    }
+  };
+  // thread-tile coordinates: groups of 4 contiguous elements, groups 64 apart (conflict-free float4)
+  auto row_of = [&](int i) { return TM >= 4 ? (i / 4) * 64 + ty * 4 + (i % 4) : ty * TM + i; };
+  auto col_of = [&](int j) { return TN >= 4 ? (j / 4) * 64 + tx * 4 + (j % 4) : tx * TN + j; };
+
+  int buf = 0;
+  if (kbeg < kend) {
+    load_tile(kbeg);
+    store_tile(0);
+  }
+  __syncthreads();
+  for (int64_t k0 = kbeg; k0 < kend; k0 += kBK) {
+    const bool has_next = k0 + kBK < kend;
+    if (has_next) load_tile(k0 + kBK);
+#pragma unroll
+    for (int kk = 0; kk < kBK; ++kk) {
+      float av[TM], bv[TN];
+#pragma unroll
+      for (int i = 0; i < TM; ++i) av[i] = As[buf][kk][row_of(i)];
+#pragma unroll
+      for (int j = 0; j < TN; ++j) bv[j] = Bs[buf][kk][col_of(j)];
+#pragma unroll
+      for (int i = 0; i < TM; ++i)
+#pragma unroll
+        for (int j = 0; j < TN; ++j) acc[i][j] = fmaf(av[i], bv[j], acc[i][j]);
+    }
+    if (has_next) store_tile(buf ^ 1);
+    __syncthreads();
+    buf ^= 1;
+  }
+
+#pragma unroll
+  for (int i = 0; i < TM; ++i) {
+    const int64_t gm = m0 + row_of(i);
+    if (gm >= g.m) continue;
+#pragma unroll
+    for (int j = 0; j < TN; ++j) {
+      const int64_t gn = n0 + col_of(j);
+      if (gn >= g.n) continue;
+      float v = g.alpha * acc[i][j];
+      if (g.splits > 1) {
+        g.ws[((int64_t)blockIdx.z * g.m + gm) * g.n + gn] = v;
+      } else {
+        if (g.accumulate) v += g.c[gm * g.ldc + gn];
+        if (g.bias) v += g.bias[gn];
+        g.c[gm * g.ldc + gn] = act_apply(v, g.act);
+      }
+    }
+  }
+}
+
+// deterministic split-K reduction (ascending split order) + epilogue
+__global__ void splitk_reduce_kernel(const GemmArgs g) {
+  const int64_t total = g.m * g.n;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total;
+       i += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t gm = i / g.n, gn = i - gm * g.n;
+    float v = 0.f;
+    for (int z = 0; z < g.splits; ++z) v += g.ws[(int64_t)z * total + i];
+    if (g.accumulate) v += g.c[gm * g.ldc + gn];
+    if (g.bias) v += g.bias[gn];
+    g.c[gm * g.ldc + gn] = act_apply(v, g.act);
+  }
+}
+
+template <int BM, int BN>
+static void launch_cfg(const GemmArgs& ga, bool akc, bool bnc, cudaStream_t st) {
+  dim3 grid((unsigned)ceil_div(ga.n, BN), (unsigned)ceil_div(ga.m, BM), (unsigned)ga.splits);
+  if (akc && bnc) sgemm_kernel<BM, BN, true, true><<<grid, kThreads, 0, st>>>(ga);
+  else if (akc && !bnc) sgemm_kernel<BM, BN, true, false><<<grid, kThreads, 0, st>>>(ga);
+  else if (!akc && bnc) sgemm_kernel<BM, BN, false, true><<<grid, kThreads, 0, st>>>(ga);
+  else sgemm_kernel<BM, BN, false, false><<<grid, kThreads, 0, st>>>(ga);
+}
+
+b2ctr_status_t gemm_fp32(const b2ctr_gemm_t* g, void* workspace, size_t workspace_bytes,
+                         cudaStream_t st) {
+  GemmArgs ga;
+  ga.a = g->a; ga.b = g->b; ga.c = g->c; ga.bias = g->bias; ga.ws = (float*)workspace;
+  ga.m = g->m; ga.n = g->n; ga.k = g->k;
+  ga.sam = g->trans_a ? 1 : g->lda;  ga.sak = g->trans_a ? g->lda : 1;
+  ga.sbk = g->trans_b ? 1 : g->ldb;  ga.sbn = g->trans_b ? g->ldb : 1;
+  ga.ldc = g->ldc; ga.alpha = g->alpha; ga.act = g->act; ga.accumulate = g->accumulate;
+  ga.splits = g->split_k > 1 ? g->split_k : 1;
+  if (ga.splits > 1) {
+    const size_t need = (size_t)ga.splits * g->m * g->n * sizeof(float);
+    if (!workspace || workspace_bytes < need) {
+      set_error("gemm: split_k=%d needs %zu workspace bytes, got %zu", ga.splits, need, workspace_bytes);
+      return B2CTR_ERR_WORKSPACE;
+    }
+  }
+  ga.k_per_split = ceil_div(ceil_div(g->k, ga.splits), kBK) * kBK;
+  const bool akc = !g->trans_a, bnc = !g->trans_b;
+  if (g->n <= 32) launch_cfg<128, 32>(ga, akc, bnc, st);
+  else if (g->n <= 64) launch_cfg<128, 64>(ga, akc, bnc, st);
+  else launch_cfg<128, 128>(ga, akc, bnc, st);
+  B2_CHECK_LAUNCH("b2ctr_gemm(fp32)");
+  if (ga.splits > 1) {
+    splitk_reduce_kernel<<<grid_for(g->m * g->n, 256, 4), 256, 0, st>>>(ga);
+    B2_CHECK_LAUNCH("b2ctr_gemm(splitk_reduce)");
+  }
+  return B2CTR_OK;
+}
+
+b2ctr_status_t gemm_bf16x3(const b2ctr_gemm_t* g, void* workspace, size_t workspace_bytes,
+                           cudaStream_t st);  // gemm_tc.cu
+size_t gemm_bf16x3_workspace_bytes(const b2ctr_gemm_t* g);
+
+}  // namespace b2ctr
+
+using namespace b2ctr;
+
+extern "C" {
+
+size_t b2ctr_gemm_workspace_bytes(const b2ctr_gemm_t* g) {
+  if (!g) return 0;
+  if (g->precision == B2CTR_GEMM_BF16X3) return gemm_bf16x3_workspace_bytes(g);
+  return g->split_k > 1 ? (size_t)g->split_k * g->m * g->n * sizeof(float) : 0;
+}
+
+b2ctr_status_t b2ctr_gemm(const b2ctr_gemm_t* g, void* workspace, size_t workspace_bytes,
+                          void* stream) {
+  B2_REQUIRE(g && g->a && g->b && g->c, "gemm: NULL descriptor or matrix pointer");
+  B2_REQUIRE(g->m >= 0 && g->n >= 0 && g->k >= 0, "gemm: negative dimension");
+  B2_REQUIRE(g->lda >= (g->trans_a ? g->m : g->k) && g->ldb >= (g->trans_b ? g->k : g->n) &&
+                 g->ldc >= g->n,
+             "gemm: leading dimension smaller than the row length");
+  B2_REQUIRE(!(g->accumulate && g->act != B2CTR_ACT_NONE), "gemm: accumulate with activation");
+  B2_REQUIRE(g->act >= B2CTR_ACT_NONE && g->act <= B2CTR_ACT_TANH, "gemm: bad activation");
+  if (g->m == 0 || g->n == 0) return B2CTR_OK;
+  if (g->precision == B2CTR_GEMM_BF16X3)
+    return gemm_bf16x3(g, workspace, workspace_bytes, (cudaStream_t)stream);
+  B2_REQUIRE(g->precision == B2CTR_GEMM_FP32, "gemm: unknown precision mode %d", g->precision);
+  return gemm_fp32(g, workspace, workspace_bytes, (cudaStream_t)stream);
+}
+
+}  // extern "C"

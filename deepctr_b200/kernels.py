@@ -1,0 +1,276 @@
+"""Thin, autograd-free wrappers: torch CUDA tensors in, C-ABI call, torch CUDA tensors out.
+
+torch only provides device memory (``torch.empty``) and the current stream handle here; every
+byte of arithmetic happens inside libb2ctr.so.  These functions are what the GPU parity tests
+call ("through the C-ABI") and what the engine (``engine.py``) builds its tape ops from.
+"""
+import ctypes as C
+
+import torch
+
+from . import _lib as L
+
+_workspace = {}
+
+
+def _require_cuda(*tensors):
+    for t in tensors:
+        if t is not None and not t.is_cuda:
+            raise L.B2ctrError("b2ctr kernels need CUDA tensors: there is no CPU fallback")
+
+
+def stream():
+    return C.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def ptr(t):
+    return C.c_void_p(t.data_ptr()) if t is not None else C.c_void_p(0)
+
+
+def workspace(nbytes, device):
+    """Grow-only scratch buffer per device (caller-provided workspace of the C-ABI)."""
+    if nbytes <= 0:
+        return None
+    key = (device.index if device.index is not None else torch.cuda.current_device())
+    buf = _workspace.get(key)
+    if buf is None or buf.numel() < nbytes:
+        buf = torch.empty(max(nbytes, 1 << 20), dtype=torch.uint8, device=device)
+        _workspace[key] = buf
+    return buf
+
+
+def idx_dtype(t):
+    if t.dtype == torch.int32:
+        return L.IDX_I32
+    if t.dtype == torch.int64:
+        return L.IDX_I64
+    raise ValueError("ids must be int32 or int64, got %s" % t.dtype)
+
+
+# ---- embedding ------------------------------------------------------------------------------
+def make_feature(table, idx, out, out_col=0, out_ld=None, maxlen=1, pool=L.POOL_NONE,
+                 mask_mode=L.MASK_NONE, length=None, weight=None, weight_mode=L.WEIGHT_NONE,
+                 hash_mode=L.HASH_NONE, idx_stride=None, src_table=None):
+    """Fill one b2ctr_feature_t.  ``idx`` is [B] / [B,1] / [B,T] (or a strided column view)."""
+    _require_cuda(table, idx, out)
+    f = L.Feature()
+    f.table = table.data_ptr()
+    f.idx = idx.data_ptr()
+    f.len = length.data_ptr() if length is not None else None
+    f.weight = weight.data_ptr() if weight is not None else None
+    f.out = out.data_ptr()
+    f.vocab = table.shape[0]
+    f.dim = table.shape[1] if table.dim() > 1 else 1
+    f.idx_stride = idx_stride if idx_stride is not None else (idx.stride(0) if idx.dim() >= 1 else 1)
+    f.out_ld = out_ld if out_ld is not None else out.stride(0)
+    f.out_col = out_col
+    f.maxlen = maxlen
+    f.idx_dtype = idx_dtype(idx)
+    f.pool = pool
+    f.mask_mode = mask_mode
+    f.hash_mode = hash_mode
+    f.weight_mode = weight_mode
+    f.src_table = src_table.data_ptr() if src_table is not None else None
+    return f
+
+
+def _feat_array(feats):
+    arr = (L.Feature * len(feats))(*feats)
+    return arr
+
+
+def embed_gather_fwd(feats, batch):
+    arr = _feat_array(feats)
+    L.check(L.lib().b2ctr_embed_gather_fwd(arr, len(feats), batch, stream()), "embed_gather_fwd")
+
+
+def embed_scatter_add(feats, batch, scale):
+    arr = _feat_array(feats)
+    L.check(L.lib().b2ctr_embed_scatter_add(arr, len(feats), batch, scale, stream()),
+            "embed_scatter_add")
+
+
+class UniformPlan(object):
+    """Host-side descriptor for the Criteo-shaped fast path; keeps ctypes arrays alive."""
+
+    def __init__(self, feats, lin_tables, dense, x, linear, fm, fm_mask):
+        self.feat_arr = _feat_array(feats)
+        self.g = L.UniformGather()
+        self.g.feats = self.feat_arr
+        if lin_tables is not None:
+            self.lin_arr = (C.c_void_p * len(feats))(*[t.data_ptr() for t in lin_tables])
+            self.g.lin_tables = self.lin_arr
+        self.g.dense = dense.data_ptr() if dense is not None else None
+        self.g.x = x.data_ptr()
+        self.g.linear = linear.data_ptr() if linear is not None else None
+        self.g.fm = fm.data_ptr() if fm is not None else None
+        self.g.ldx = x.stride(0)
+        self.g.dense_ld = dense.stride(0) if dense is not None else 0
+        self.g.nfeat = len(feats)
+        self.g.ndense = dense.shape[1] if dense is not None else 0
+        self.g.fm_mask[0] = fm_mask & 0xFFFFFFFFFFFFFFFF
+        self.g.fm_mask[1] = 0
+
+
+def embed_gather_uniform_fwd(plan, batch):
+    L.check(L.lib().b2ctr_embed_gather_uniform_fwd(C.byref(plan.g), batch, stream()),
+            "embed_gather_uniform_fwd")
+
+
+def embed_scatter_uniform_bwd(plan, dx, dfm, dlinear, scale, lin_scale, batch):
+    L.check(L.lib().b2ctr_embed_scatter_uniform_bwd(C.byref(plan.g), ptr(dx), ptr(dfm), ptr(dlinear),
+                                                    scale, lin_scale, batch, stream()),
+            "embed_scatter_uniform_bwd")
+
+
+def hash64(ids, num_buckets, mask_zero):
+    _require_cuda(ids)
+    ids = ids.contiguous()
+    out = torch.empty(ids.shape, dtype=torch.int64, device=ids.device)
+    L.check(L.lib().b2ctr_hash64(ptr(ids), idx_dtype(ids), ids.numel(), num_buckets,
+                                 1 if mask_zero else 0, ptr(out), stream()), "hash64")
+    return out
+
+
+def init_normal(dst, mean, std, seed):
+    _require_cuda(dst)
+    L.check(L.lib().b2ctr_init_normal(ptr(dst), dst.numel(), mean, std, seed, stream()), "init_normal")
+    return dst
+
+
+# ---- GEMM -----------------------------------------------------------------------------------
+def gemm(a, b, c=None, bias=None, trans_a=False, trans_b=False, act=L.ACT_NONE, accumulate=False,
+         precision=L.GEMM_FP32, split_k=1, alpha=1.0, m=None, n=None, k=None):
+    """C[M,N] = act(alpha * op(A) @ op(B) + bias) on 2-D row-major (possibly ld-padded) tensors."""
+    _require_cuda(a, b, c, bias)
+    if m is None:
+        m = a.shape[1] if trans_a else a.shape[0]
+    if k is None:
+        k = a.shape[0] if trans_a else a.shape[1]
+    if n is None:
+        n = b.shape[0] if trans_b else b.shape[1]
+    if c is None:
+        c = torch.empty((m, n), dtype=torch.float32, device=a.device)
+    g = L.Gemm()
+    g.a, g.b, g.c = a.data_ptr(), b.data_ptr(), c.data_ptr()
+    g.bias = bias.data_ptr() if bias is not None else None
+    g.m, g.n, g.k = m, n, k
+    g.lda, g.ldb, g.ldc = a.stride(0), b.stride(0), c.stride(0)
+    g.trans_a, g.trans_b = int(trans_a), int(trans_b)
+    g.act, g.accumulate, g.precision, g.split_k, g.alpha = act, int(accumulate), precision, split_k, alpha
+    nbytes = L.lib().b2ctr_gemm_workspace_bytes(C.byref(g))
+    ws = workspace(nbytes, a.device)
+    L.check(L.lib().b2ctr_gemm(C.byref(g), ptr(ws), nbytes if ws is not None else 0, stream()), "gemm")
+    return c
+
+
+# ---- elementwise ----------------------------------------------------------------------------
+def bias_act_bwd(dy, y, act, want_dz=True, want_dbias=True, m=None, n=None):
+    _require_cuda(dy, y)
+    if m is None:
+        m, n = dy.shape[0], dy.shape[1]
+    ld = dy.stride(0)
+    dz = torch.empty_like(dy) if want_dz else None
+    dbias = torch.empty((n,), dtype=torch.float32, device=dy.device) if want_dbias else None
+    nbytes = L.lib().b2ctr_bias_act_bwd_workspace_bytes(m, n) if want_dbias else 0
+    ws = workspace(nbytes, dy.device)
+    L.check(L.lib().b2ctr_bias_act_bwd(ptr(dy), ptr(y), ptr(dz), ptr(dbias), m, n, ld, act, ptr(ws),
+                                       nbytes, stream()), "bias_act_bwd")
+    return dz, dbias
+
+
+def act_fwd(x, act, out=None):
+    _require_cuda(x)
+    out = torch.empty_like(x) if out is None else out
+    L.check(L.lib().b2ctr_act_fwd(ptr(x), ptr(out), x.numel(), act, stream()), "act_fwd")
+    return out
+
+
+def add_n(ins, scales=None, out=None):
+    _require_cuda(*ins)
+    out = torch.empty_like(ins[0]) if out is None else out
+    arr = (C.c_void_p * len(ins))(*[t.data_ptr() for t in ins])
+    sc = (C.c_float * len(ins))(*(scales if scales is not None else [1.0] * len(ins)))
+    L.check(L.lib().b2ctr_add_n(arr, sc, len(ins), ptr(out), out.numel(), stream()), "add_n")
+    return out
+
+
+def axpy(x, y, alpha=1.0):
+    _require_cuda(x, y)
+    L.check(L.lib().b2ctr_axpy(ptr(x), ptr(y), alpha, x.numel(), stream()), "axpy")
+    return y
+
+
+def fill(dst, value):
+    _require_cuda(dst)
+    L.check(L.lib().b2ctr_fill(ptr(dst), value, dst.numel(), stream()), "fill")
+    return dst
+
+
+def copy2d(src, ld_src, dst, ld_dst, rows, cols, accumulate=False, src_off=0, dst_off=0):
+    _require_cuda(src, dst)
+    sp = C.c_void_p(src.data_ptr() + 4 * src_off)
+    dp = C.c_void_p(dst.data_ptr() + 4 * dst_off)
+    L.check(L.lib().b2ctr_copy2d(sp, ld_src, dp, ld_dst, rows, cols, int(accumulate), stream()), "copy2d")
+    return dst
+
+
+def rowsum(x, rows, cols, ld=None):
+    _require_cuda(x)
+    out = torch.empty((rows,), dtype=torch.float32, device=x.device)
+    L.check(L.lib().b2ctr_rowsum(ptr(x), ld if ld is not None else x.stride(0), ptr(out), rows, cols,
+                                 stream()), "rowsum")
+    return out
+
+
+def fm_fwd(x, nfield, dim, ldx=None):
+    _require_cuda(x)
+    batch = x.shape[0]
+    out = torch.empty((batch,), dtype=torch.float32, device=x.device)
+    L.check(L.lib().b2ctr_fm_fwd(ptr(x), ldx if ldx is not None else x.stride(0), nfield, dim, ptr(out),
+                                 batch, stream()), "fm_fwd")
+    return out
+
+
+def fm_bwd(x, nfield, dim, dout, dx=None, accumulate=False, ldx=None):
+    _require_cuda(x, dout)
+    batch = x.shape[0]
+    ldx = ldx if ldx is not None else x.stride(0)
+    if dx is None:
+        dx = torch.empty_like(x)
+        accumulate = False
+    L.check(L.lib().b2ctr_fm_bwd(ptr(x), ldx, nfield, dim, ptr(dout), ptr(dx), dx.stride(0),
+                                 int(accumulate), batch, stream()), "fm_bwd")
+    return dx
+
+
+# ---- head / loss / optimizers ---------------------------------------------------------------
+def predict_loss(logit, bias=None, labels=None, task=L.TASK_BINARY, want_grad=False):
+    """Returns (pred[B], dlogit[B] | None, dbias[1] | None, loss_sum[1] | None)."""
+    _require_cuda(logit, bias, labels)
+    batch = logit.numel()
+    pred = torch.empty((batch,), dtype=torch.float32, device=logit.device)
+    dlogit = torch.empty((batch,), dtype=torch.float32, device=logit.device) if want_grad else None
+    acc = torch.zeros((2,), dtype=torch.float32, device=logit.device) if labels is not None else None
+    loss_sum = acc[0:1] if acc is not None else None
+    dbias = acc[1:2] if (acc is not None and want_grad and bias is not None) else None
+    L.check(L.lib().b2ctr_predict_loss(ptr(logit), ptr(bias), ptr(labels), ptr(pred), ptr(dlogit),
+                                       ptr(dbias), ptr(loss_sum), batch, task, stream()), "predict_loss")
+    return pred, dlogit, dbias, loss_sum
+
+
+def sgd_step(w, g, lr, l2=0.0):
+    _require_cuda(w, g)
+    L.check(L.lib().b2ctr_sgd_step(ptr(w), ptr(g), lr, l2, w.numel(), stream()), "sgd_step")
+
+
+def adam_step(w, g, m, v, lr, step, beta1=0.9, beta2=0.999, eps=1e-7, l2=0.0):
+    _require_cuda(w, g, m, v)
+    L.check(L.lib().b2ctr_adam_step(ptr(w), ptr(g), ptr(m), ptr(v), lr, beta1, beta2, eps, l2, step,
+                                    w.numel(), stream()), "adam_step")
+
+
+def adagrad_step(w, g, acc, lr, eps=1e-7, l2=0.0):
+    _require_cuda(w, g, acc)
+    L.check(L.lib().b2ctr_adagrad_step(ptr(w), ptr(g), ptr(acc), lr, eps, l2, w.numel(), stream()),
+            "adagrad_step")

@@ -1,0 +1,241 @@
+/*
+ * b2ctr.h — C-ABI of libb2ctr.so: the B200 (sm_100a) CTR forward/backward hot path.
+ *
+ * The reference (shenweichen/DeepCTR, pure Python over TensorFlow) has no FFI of its own
+ * (SURVEY.md §8b).  Each entry point below is what a maintainer would bind in place of the
+ * TensorFlow ops a `deepctr.layers` operator dispatches to; the reference interface it
+ * replaces is cited as deepctr/<file>:<line> next to every declaration.
+ *
+ * Conventions
+ *   - every function returns b2ctr_status_t (0 = OK, <0 = error); b2ctr_last_error() returns a
+ *     thread-local message for the last non-zero status;
+ *   - all data pointers are DEVICE pointers owned by the caller (they are never retained or
+ *     freed); descriptor structs are HOST structs passed by pointer and copied by value into
+ *     the launch (no hidden allocations, no hidden synchronisation);
+ *   - `stream` is a cudaStream_t passed as void*; every call is asynchronous on that stream;
+ *   - tensors are dense row-major fp32 unless a leading dimension (`ld*`, in elements) is given;
+ *   - no torch / python types anywhere in this header.
+ */
+#ifndef B2CTR_H_
+#define B2CTR_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#if defined(_WIN32)
+#define B2CTR_API
+#else
+#define B2CTR_API __attribute__((visibility("default")))
+#endif
+
+typedef int32_t b2ctr_status_t;
+enum {
+  B2CTR_OK = 0,
+  B2CTR_ERR_INVALID_ARG = -1, /* bad shape / null pointer / unsupported combination -> ValueError */
+  B2CTR_ERR_CUDA = -2,        /* launch or runtime failure -> RuntimeError */
+  B2CTR_ERR_UNSUPPORTED = -3, /* valid request the library cannot serve (e.g. alignment) */
+  B2CTR_ERR_WORKSPACE = -4    /* workspace missing or too small */
+};
+
+/* version / diagnostics -------------------------------------------------------------------- */
+B2CTR_API int32_t b2ctr_abi_version(void);
+B2CTR_API const char* b2ctr_last_error(void);
+/* number of kernels launched by this library since load (bench.py's gpu_launches evidence) */
+B2CTR_API int64_t b2ctr_launch_count(void);
+B2CTR_API void b2ctr_reset_launch_count(void);
+
+/* ------------------------------------------------------------------------------------------ */
+/* 1. Embedding gather / scatter-update                                                        */
+/*    replaces: tf.keras.layers.Embedding call in deepctr/inputs.py:101-130 (embedding_lookup,  */
+/*    varlen_embedding_lookup), the pooling of deepctr/inputs.py:133-158 +                      */
+/*    deepctr/layers/sequence.py:41-197, the Hash op of deepctr/layers/utils.py:89-112, and     */
+/*    the orchestration of deepctr/feature_column.py:213-233 (input_from_feature_columns).      */
+/* ------------------------------------------------------------------------------------------ */
+
+enum { B2CTR_IDX_I32 = 0, B2CTR_IDX_I64 = 1 };
+enum { B2CTR_POOL_NONE = 0, /* emit the [T,dim] sequence, no pooling (DIN keys)      */
+       B2CTR_POOL_SUM = 1, B2CTR_POOL_MEAN = 2, B2CTR_POOL_MAX = 3 };
+enum { B2CTR_MASK_NONE = 0,   /* every position valid                                  */
+       B2CTR_MASK_ZERO_ID = 1,/* Keras mask_zero: position valid iff raw id != 0       */
+       B2CTR_MASK_LENGTH = 2  /* tf.sequence_mask: position t valid iff t < len[b]     */ };
+enum { B2CTR_HASH_NONE = 0,
+       B2CTR_HASH_FARM = 1,          /* Fingerprint64(decimal(id)) % num_buckets                 */
+       B2CTR_HASH_FARM_MASK_ZERO = 2 /* (Fingerprint64 % (num_buckets-1) + 1) * (id != 0)       */ };
+enum { B2CTR_WEIGHT_NONE = 0, B2CTR_WEIGHT_RAW = 1, /* where(mask, w, 0)                        */
+       B2CTR_WEIGHT_SOFTMAX = 2                     /* softmax_t(where(mask, w, -2^32+1))        */ };
+
+/* One feature column bound to one table for one launch.  sizeof == 112. */
+typedef struct b2ctr_feature {
+  float* table;          /* [vocab, dim] fp32 rows (read in fwd, updated in bwd)                 */
+  const void* idx;       /* ids: element (b, t) at idx[b*idx_stride + t]                          */
+  const int32_t* len;    /* [B] valid lengths (mask_mode LENGTH), else NULL                       */
+  const float* weight;   /* [B, maxlen] per-position weights (weight_mode != NONE), else NULL    */
+  float* out;            /* fwd: destination; bwd: incoming gradient of the same layout          */
+  int64_t vocab;         /* rows in table; also num_buckets for hashing                          */
+  int64_t idx_stride;    /* elements between consecutive samples in idx                          */
+  int64_t out_ld;        /* elements between consecutive samples in out                          */
+  int32_t out_col;       /* first column of this feature inside out rows                         */
+  int32_t dim;           /* embedding_dim                                                        */
+  int32_t maxlen;        /* 1 for SparseFeat, T for VarLenSparseFeat                             */
+  int32_t idx_dtype;     /* B2CTR_IDX_*                                                          */
+  int32_t pool;          /* B2CTR_POOL_*                                                         */
+  int32_t mask_mode;     /* B2CTR_MASK_*                                                         */
+  int32_t hash_mode;     /* B2CTR_HASH_*                                                         */
+  int32_t weight_mode;   /* B2CTR_WEIGHT_*                                                       */
+  const float* src_table;/* scatter only: table holding the FORWARD rows when `table` is a separate
+                            gradient buffer (needed by max pooling to re-find the arg-max); NULL = table */
+  int32_t reserved[2];
+} b2ctr_feature_t;
+
+#define B2CTR_MAX_FEATURES 128
+
+/* Generic fused multi-table gather: any mix of single / pooled / sequence / hashed / weighted
+ * features of any dim, one launch.  Pooled sums accumulate in ascending-t order in fp32
+ * (bit-exact against oracle/seqpool). */
+B2CTR_API b2ctr_status_t b2ctr_embed_gather_fwd(const b2ctr_feature_t* feats, int32_t nfeat,
+                                               int64_t batch, void* stream);
+
+/* Generic scatter: table[id] += scale * d(out) routed through the pooling Jacobian.
+ * scale = -lr gives fused SGD; scale = 1 with `table` pointing at a zeroed [vocab,dim] buffer
+ * gives a dense gradient (for dense optimizers / l2 on the whole table).
+ * Duplicate ids are combined with fp32 atomics (vector red.global.add.v4.f32).            */
+B2CTR_API b2ctr_status_t b2ctr_embed_scatter_add(const b2ctr_feature_t* feats, int32_t nfeat,
+                                                int64_t batch, float scale, void* stream);
+
+/* Criteo-shaped fast path (all features single-valued, same dim, dim % 4 == 0, dim <= 128):
+ * one warp per sample gathers F rows with 128-bit loads into x[b, f*dim : (f+1)*dim], copies
+ * `dense` into x[b, F*dim : F*dim+ndense], zero-fills up to ldx, and in the same pass emits
+ *   linear[b] = sum_f lin_table_f[id_f]                 (get_linear_logit, feature_column.py:171-210)
+ *   fm[b]     = 0.5 * sum_e((sum_f x)^2 - sum_f x^2)    (FM, layers/interaction.py:597-602)
+ * over the features whose bit is set in fm_mask (bit f of fm_mask[f/64]).
+ * feats[f].{table,idx,idx_stride,idx_dtype,vocab,dim} are used; lin_tables may be NULL. */
+typedef struct b2ctr_uniform_gather {
+  const b2ctr_feature_t* feats;
+  float* const* lin_tables;     /* host array [nfeat] of device ptrs to [vocab] fp32, or NULL   */
+  const float* dense;           /* [B, ndense] (ld = dense_ld) or NULL                          */
+  float* x;                     /* [B, ldx] output / saved activations                          */
+  float* linear;                /* [B] or NULL                                                  */
+  float* fm;                    /* [B] or NULL                                                  */
+  int64_t ldx;
+  int64_t dense_ld;
+  int32_t nfeat;
+  int32_t ndense;
+  uint64_t fm_mask[2];
+} b2ctr_uniform_gather_t;
+
+B2CTR_API b2ctr_status_t b2ctr_embed_gather_uniform_fwd(const b2ctr_uniform_gather_t* g,
+                                                       int64_t batch, void* stream);
+
+/* Backward of the above fused with the row update:
+ *   g_row(b,f) = dx[b, f*dim:(f+1)*dim] + dfm[b] * (S_b - x[b, f*dim:...])   (FM Jacobian, App. A.6)
+ *   table_f[id] += scale * g_row ;  lin_table_f[id] += lin_scale * dlinear[b]
+ * dx, dfm, dlinear may each be NULL.  ddense (if not NULL) receives dx[:, F*dim : F*dim+ndense]. */
+B2CTR_API b2ctr_status_t b2ctr_embed_scatter_uniform_bwd(const b2ctr_uniform_gather_t* g,
+                                                        const float* dx, const float* dfm,
+                                                        const float* dlinear, float scale,
+                                                        float lin_scale, int64_t batch,
+                                                        void* stream);
+
+/* Hash (deepctr/layers/utils.py:89-112): ids -> int64 buckets, FarmHash Fingerprint64 of the
+ * decimal ASCII form.  mask_zero: 0 stays 0, others land in [1, num_buckets).               */
+B2CTR_API b2ctr_status_t b2ctr_hash64(const void* ids, int32_t idx_dtype, int64_t n,
+                                     int64_t num_buckets, int32_t mask_zero, int64_t* out,
+                                     void* stream);
+
+/* On-device table initialisation: table[i] = mean + std * N(0,1), Philox4x32-10 keyed by seed
+ * (RandomNormal(0, 1e-4, seed=2020), deepctr/feature_column.py:46-47; needed because a
+ * 26 x 100M x 128 table set cannot be initialised on the host). */
+B2CTR_API b2ctr_status_t b2ctr_init_normal(float* dst, int64_t n, float mean, float std,
+                                          uint64_t seed, void* stream);
+
+/* ------------------------------------------------------------------------------------------ */
+/* 2. Dense linear algebra: C = epilogue(op(A) @ op(B))                                        */
+/*    replaces tf.tensordot / tf.matmul in deepctr/layers/core.py:193-195 (DNN), :106 (LAU),   */
+/*    deepctr/layers/interaction.py:754-757 (InteractingLayer projections), :414-418 (CrossNet)*/
+/* ------------------------------------------------------------------------------------------ */
+enum { B2CTR_ACT_NONE = 0, B2CTR_ACT_RELU = 1, B2CTR_ACT_SIGMOID = 2, B2CTR_ACT_TANH = 3 };
+enum { B2CTR_GEMM_FP32 = 0,  /* exact fp32 FFMA path (CUDA cores)                              */
+       B2CTR_GEMM_BF16X3 = 1 /* tcgen05 tensor cores, 3-term split-bf16 (~2^-17 rel. error)    */ };
+
+typedef struct b2ctr_gemm {
+  const float* a; const float* b; float* c;
+  const float* bias;       /* [N] added to every row, or NULL                                  */
+  int64_t m, n, k;
+  int64_t lda, ldb, ldc;   /* leading dims of the STORED matrices (row-major)                  */
+  int32_t trans_a;         /* 0: A stored [M,K]; 1: A stored [K,M]                             */
+  int32_t trans_b;         /* 0: B stored [K,N]; 1: B stored [N,K]                             */
+  int32_t act;             /* B2CTR_ACT_* applied after bias                                   */
+  int32_t accumulate;      /* 1: C += result (before act; act must be NONE)                    */
+  int32_t precision;       /* B2CTR_GEMM_*                                                     */
+  int32_t split_k;         /* >1: split the K loop over this many CTAs (needs workspace)       */
+  float alpha;             /* scales op(A)@op(B)                                               */
+  int32_t reserved;
+} b2ctr_gemm_t;
+
+B2CTR_API size_t b2ctr_gemm_workspace_bytes(const b2ctr_gemm_t* g);
+B2CTR_API b2ctr_status_t b2ctr_gemm(const b2ctr_gemm_t* g, void* workspace, size_t workspace_bytes,
+                                   void* stream);
+
+/* ------------------------------------------------------------------------------------------ */
+/* 3. Elementwise / reductions                                                                 */
+/* ------------------------------------------------------------------------------------------ */
+/* dz = dy * act'(y) (y = activation OUTPUT), dbias[n] = sum_m dz[m,n] (deterministic two-pass)  */
+B2CTR_API size_t b2ctr_bias_act_bwd_workspace_bytes(int64_t m, int64_t n);
+B2CTR_API b2ctr_status_t b2ctr_bias_act_bwd(const float* dy, const float* y, float* dz,
+                                           float* dbias, int64_t m, int64_t n, int64_t ld,
+                                           int32_t act, void* workspace, size_t workspace_bytes,
+                                           void* stream);
+/* y = act(x) elementwise over n contiguous elements */
+B2CTR_API b2ctr_status_t b2ctr_act_fwd(const float* x, float* y, int64_t n, int32_t act,
+                                      void* stream);
+/* out[i] = sum_j in_j[i] * (scale_j), j < nin <= 8, in_j may alias out */
+B2CTR_API b2ctr_status_t b2ctr_add_n(const float* const* ins, const float* scales, int32_t nin,
+                                    float* out, int64_t n, void* stream);
+/* y[i] += alpha * x[i] */
+B2CTR_API b2ctr_status_t b2ctr_axpy(const float* x, float* y, float alpha, int64_t n, void* stream);
+/* strided 2-D copy: dst[r*ld_dst + c] (+)= src[r*ld_src + c], r<rows, c<cols  (concat / slice)  */
+B2CTR_API b2ctr_status_t b2ctr_copy2d(const float* src, int64_t ld_src, float* dst, int64_t ld_dst,
+                                     int64_t rows, int64_t cols, int32_t accumulate, void* stream);
+/* out[r] = sum_c x[r*ld + c] (ascending c, fp32)   (Linear mode 0/2, layers/utils.py:160-171) */
+B2CTR_API b2ctr_status_t b2ctr_rowsum(const float* x, int64_t ld, float* out, int64_t rows,
+                                     int64_t cols, void* stream);
+B2CTR_API b2ctr_status_t b2ctr_fill(float* dst, float value, int64_t n, void* stream);
+
+/* FM second-order term on [B,F,E] (deepctr/layers/interaction.py:588-604) and its Jacobian */
+B2CTR_API b2ctr_status_t b2ctr_fm_fwd(const float* x, int64_t ldx, int32_t nfield, int32_t dim,
+                                     float* out, int64_t batch, void* stream);
+B2CTR_API b2ctr_status_t b2ctr_fm_bwd(const float* x, int64_t ldx, int32_t nfield, int32_t dim,
+                                     const float* dout, float* dx, int64_t lddx, int32_t accumulate,
+                                     int64_t batch, void* stream);
+
+/* ------------------------------------------------------------------------------------------ */
+/* 4. Prediction head, loss, optimizers                                                         */
+/* ------------------------------------------------------------------------------------------ */
+/* PredictionLayer (deepctr/layers/core.py:250-259) + Keras binary_crossentropy / mse
+ *  in one pass:
+ *   z = logit[b] + (bias ? *bias : 0);  p = task==binary ? sigmoid(z) : z;  pred[b] = p
+ *   loss_sum[0] += sum_b l(y_b, p_b)  (caller zeroes it; divide by B on the host side)
+ *   dlogit[b] = (1/B) * dl/dz   (dlogit / labels / loss_sum may be NULL for inference)        */
+enum { B2CTR_TASK_BINARY = 0, B2CTR_TASK_REGRESSION = 1 };
+B2CTR_API b2ctr_status_t b2ctr_predict_loss(const float* logit, const float* bias,
+                                           const float* labels, float* pred, float* dlogit,
+                                           float* dbias, float* loss_sum, int64_t batch,
+                                           int32_t task, void* stream);
+
+B2CTR_API b2ctr_status_t b2ctr_sgd_step(float* w, const float* g, float lr, float l2, int64_t n,
+                                       void* stream);
+/* Keras Adam (lr 1e-3, b1 .9, b2 .999, eps 1e-7): step counts from 1 */
+B2CTR_API b2ctr_status_t b2ctr_adam_step(float* w, const float* g, float* m, float* v, float lr,
+                                        float beta1, float beta2, float eps, float l2,
+                                        int64_t step, int64_t n, void* stream);
+B2CTR_API b2ctr_status_t b2ctr_adagrad_step(float* w, const float* g, float* acc, float lr,
+                                           float eps, float l2, int64_t n, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* B2CTR_H_ */

@@ -1,0 +1,177 @@
+"""GPU parity: GEMM / elementwise / FM / head / optimizer kernels through the C-ABI vs torch-CPU fp32."""
+import numpy as np
+import pytest
+import torch
+
+from oracle import ops as O
+
+pytestmark = pytest.mark.gpu
+
+
+def _kern():
+    from deepctr_b200 import kernels as K, _lib as L
+    return K, L
+
+
+def _r(rng, *shape):
+    return torch.tensor(rng.normal(size=shape).astype(np.float32))
+
+
+@pytest.mark.parametrize("m,n,k", [(1, 1, 1), (257, 256, 845), (130, 64, 128), (1000, 1, 64),
+                                   (64, 300, 7)])
+@pytest.mark.parametrize("ta,tb", [(False, False), (False, True), (True, False), (True, True)])
+def test_gemm_fp32_layouts(cuda, m, n, k, ta, tb):
+    K, L = _kern()
+    rng = np.random.RandomState(m * 7 + n)
+    a = _r(rng, *((k, m) if ta else (m, k)))
+    b = _r(rng, *((n, k) if tb else (k, n)))
+    bias = _r(rng, n)
+    want = torch.relu((a.t() if ta else a).double() @ (b.t() if tb else b).double() + bias.double()).float()
+    got = K.gemm(a.to(cuda), b.to(cuda), bias=bias.to(cuda), trans_a=ta, trans_b=tb, act=L.ACT_RELU, m=m, n=n, k=k)
+    torch.testing.assert_close(got.cpu(), want, rtol=1e-4, atol=1e-4)
+
+
+def test_gemm_splitk_accumulate_and_ld(cuda):
+    K, L = _kern()
+    rng = np.random.RandomState(3)
+    m, n, k = 845, 256, 4099          # wgrad shape: reduction over the batch
+    x = _r(rng, k, 848)[:, :m]        # stored [K, M] with ld 848 (K-padded activations)
+    dy = _r(rng, k, n)
+    c0 = _r(rng, m, n)
+    want = (c0.double() + 0.5 * (x.t().double() @ dy.double())).float()
+    xd = _r(rng, k, 848).to(cuda)
+    xd[:, :m] = x.to(cuda)
+    c = c0.to(cuda)
+    K.gemm(xd, dy.to(cuda), c=c, trans_a=True, accumulate=True, split_k=16, alpha=0.5, m=m, n=n, k=k)
+    torch.testing.assert_close(c.cpu(), want, rtol=1e-4, atol=2e-4)
+    # determinism of the split-K reduction
+    c2 = c0.to(cuda)
+    K.gemm(xd, dy.to(cuda), c=c2, trans_a=True, accumulate=True, split_k=16, alpha=0.5, m=m, n=n, k=k)
+    assert torch.equal(c, c2)
+
+
+def test_gemm_rejects_bad_arguments(cuda):
+    K, L = _kern()
+    a = torch.zeros((4, 4), device=cuda)
+    with pytest.raises(ValueError):
+        K.gemm(a, a, act=L.ACT_RELU, accumulate=True)
+    with pytest.raises(L.B2ctrError):
+        K.gemm(a, a, precision=99)
+
+
+@pytest.mark.parametrize("act", ["relu", "sigmoid", "tanh", None])
+def test_bias_act_bwd(cuda, act):
+    K, L = _kern()
+    rng = np.random.RandomState(4)
+    m, n = 1031, 200
+    z = _r(rng, m, n).requires_grad_(True)
+    y = O._ACT[act](z)
+    dy = _r(rng, m, n)
+    (y * dy).sum().backward()
+    dz, db = K.bias_act_bwd(dy.to(cuda), y.detach().to(cuda), L.ACT_BY_NAME[act])
+    torch.testing.assert_close(dz.cpu(), z.grad, rtol=1e-5, atol=1e-6)
+    torch.testing.assert_close(db.cpu(), z.grad.sum(0), rtol=1e-4, atol=1e-4)
+
+
+def test_act_fwd_add_axpy_copy_rowsum_fill(cuda):
+    K, L = _kern()
+    rng = np.random.RandomState(5)
+    x = _r(rng, 1000, 37)
+    xd = x.to(cuda)
+    for name in ["relu", "sigmoid", "tanh"]:
+        torch.testing.assert_close(K.act_fwd(xd, L.ACT_BY_NAME[name]).cpu(), O._ACT[name](x),
+                                   rtol=1e-6, atol=1e-6)
+    y = _r(rng, 1000, 37)
+    got = K.add_n([xd, y.to(cuda), xd], scales=[1.0, -2.0, 0.5]).cpu()
+    torch.testing.assert_close(got, 1.5 * x - 2 * y, rtol=1e-6, atol=1e-6)
+    yd = y.to(cuda)
+    K.axpy(xd, yd, 0.25)
+    torch.testing.assert_close(yd.cpu(), y + 0.25 * x, rtol=1e-6, atol=1e-6)
+    # concat two blocks into a wider buffer, then slice-accumulate back
+    dst = torch.zeros((1000, 80), device=cuda)
+    K.copy2d(xd, 37, dst, 80, 1000, 37, dst_off=4)
+    assert torch.equal(dst[:, 4:41].cpu(), x)
+    K.copy2d(dst, 80, xd, 37, 1000, 37, accumulate=True, src_off=4)
+    assert torch.equal(xd.cpu(), 2 * x)
+    v4 = _r(rng, 64, 32).to(cuda)
+    dst4 = torch.zeros((64, 64), device=cuda)
+    K.copy2d(v4, 32, dst4, 64, 64, 32, dst_off=32)
+    assert torch.equal(dst4[:, 32:], v4)
+    torch.testing.assert_close(K.rowsum(v4, 64, 32).cpu(), v4.cpu().sum(1), rtol=1e-5, atol=1e-5)
+    f = torch.empty(1001, device=cuda)
+    K.fill(f, 3.5)
+    assert torch.all(f == 3.5)
+
+
+@pytest.mark.parametrize("F,E", [(26, 32), (4, 3), (7, 40)])
+def test_fm_fwd_bwd(cuda, F, E):
+    K, L = _kern()
+    rng = np.random.RandomState(6)
+    B = 333
+    x = _r(rng, B, F, E).requires_grad_(True)
+    out = O.fm(x)
+    g = _r(rng, B)
+    (out[:, 0] * g).sum().backward()
+    xd = x.detach().reshape(B, F * E).to(cuda)
+    torch.testing.assert_close(K.fm_fwd(xd, F, E).cpu(), out[:, 0].detach(), rtol=1e-4, atol=1e-4)
+    dx = K.fm_bwd(xd, F, E, g.to(cuda))
+    torch.testing.assert_close(dx.cpu().reshape(B, F, E), x.grad, rtol=1e-4, atol=1e-4)
+    # closed form of SURVEY.md section 8c: FM == sum_{i<j} <v_i, v_j>
+    xx = x.detach().double()
+    pair = sum((xx[:, i] * xx[:, j]).sum(-1) for i in range(F) for j in range(i + 1, F))
+    torch.testing.assert_close(K.fm_fwd(xd, F, E).cpu().double(), pair, rtol=1e-4, atol=1e-4)
+
+
+@pytest.mark.parametrize("task", ["binary", "regression"])
+def test_predict_loss(cuda, task):
+    K, L = _kern()
+    rng = np.random.RandomState(7)
+    B = 4097
+    logit = (_r(rng, B) * 3).requires_grad_(True)
+    logit.data[0], logit.data[1] = 40.0, -40.0      # saturated: exercises the clip branch
+    bias = torch.tensor([0.3], requires_grad=True)
+    y = torch.tensor((rng.rand(B) < 0.25).astype(np.float32))
+    p = O.prediction(logit[:, None], bias, task)
+    loss = O.binary_crossentropy(y, p) if task == "binary" else O.mse(y, p)
+    loss.backward()
+    t = L.TASK_BINARY if task == "binary" else L.TASK_REGRESSION
+    pred, dlogit, dbias, lsum = K.predict_loss(logit.detach().to(cuda), bias.detach().to(cuda), y.to(cuda),
+                                               t, want_grad=True)
+    torch.testing.assert_close(pred.cpu(), p.detach()[:, 0], rtol=1e-5, atol=1e-6)
+    torch.testing.assert_close(lsum.cpu() / B, loss.detach().reshape(1), rtol=1e-4, atol=1e-6)
+    torch.testing.assert_close(dlogit.cpu(), logit.grad, rtol=1e-4, atol=1e-9)
+    torch.testing.assert_close(dbias.cpu(), bias.grad, rtol=1e-3, atol=1e-7)
+    pred2, _, _, _ = K.predict_loss(logit.detach().to(cuda), None, None, t)
+    torch.testing.assert_close(pred2.cpu(), O.prediction(logit.detach()[:, None], None, task)[:, 0],
+                               rtol=1e-5, atol=1e-6)
+
+
+def test_optimizers(cuda):
+    K, L = _kern()
+    rng = np.random.RandomState(8)
+    n = 5003
+    w0, g = _r(rng, n), _r(rng, n)
+    # SGD (+ l2: d/dw l2*w^2 = 2*l2*w, Keras regularizers.l2)
+    w = w0.to(cuda)
+    K.sgd_step(w, g.to(cuda), 0.1, 0.01)
+    torch.testing.assert_close(w.cpu(), w0 - 0.1 * (g + 0.02 * w0), rtol=1e-6, atol=1e-6)
+    # Adam: 3 steps vs torch.optim.Adam(eps=1e-7) - Keras places eps outside the bias correction
+    wt = w0.clone().double()
+    m = torch.zeros(n).double()
+    v = torch.zeros(n).double()
+    w = w0.to(cuda)
+    md, vd = torch.zeros(n, device=cuda), torch.zeros(n, device=cuda)
+    for step in range(1, 4):
+        gs = (g * step).double()
+        m = 0.9 * m + 0.1 * gs
+        v = 0.999 * v + 0.001 * gs * gs
+        lr_t = 1e-3 * np.sqrt(1 - 0.999 ** step) / (1 - 0.9 ** step)
+        wt = wt - lr_t * m / (v.sqrt() + 1e-7)
+        K.adam_step(w, (g * step).to(cuda), md, vd, 1e-3, step)
+    torch.testing.assert_close(w.cpu().double(), wt, rtol=1e-5, atol=1e-6)
+    # Adagrad
+    w = w0.to(cuda)
+    acc = torch.full((n,), 0.1, device=cuda)
+    K.adagrad_step(w, g.to(cuda), acc, 0.01)
+    a = 0.1 + g * g
+    torch.testing.assert_close(w.cpu(), w0 - 0.01 * g / (a.sqrt() + 1e-7), rtol=1e-5, atol=1e-6)

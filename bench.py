@@ -1,0 +1,360 @@
+#!/usr/bin/env python
+"""bench.py - samples/sec of one DeepFM training step (fwd + loss + bwd + update) on synthetic
+Criteo-shaped batches (BASELINE.json configs[1]: 26 tables x 1M rows, emb_dim 32, batch 65536).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference] [--config c2|c2small]
+
+Prints ONE JSON line (see the task contract): `value` = device-timed whole-job samples/s with the
+batch already resident in HBM; `e2e` = the same step through the public API
+(`Model.train_on_batch(host arrays)`) including pinned-H2D of the inputs and the D2H read of the loss;
+`roofline` = the dominant kernel against the measured peaks in MEASURED_PEAKS.json; `cpu_baseline` =
+the CPU oracle (torch-CPU restatement of the reference math) on a bounded sample.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+CONFIGS = {
+    # BASELINE.json configs[1]
+    "c2": dict(workload="DeepFM synthetic Criteo: 26 tables x 1M rows, emb_dim=32, batch=65536, 13 dense",
+               n_sparse=26, n_dense=13, vocab=1000000, dim=32, batch=65536, hidden=(256, 128, 64)),
+    # tiny variant for CPU smoke runs of this script
+    "c2small": dict(workload="DeepFM synthetic Criteo (small): 26 tables x 10k rows, emb_dim=32, batch=4096",
+                    n_sparse=26, n_dense=13, vocab=10000, dim=32, batch=4096, hidden=(256, 128, 64)),
+}
+LR = 0.01
+N_BATCHES = 4      # distinct pre-generated batches cycled through the timed steps
+
+
+def feature_columns(cfg):
+    from deepctr_b200.feature_column import SparseFeat, DenseFeat
+    cols = [SparseFeat("C%d" % (i + 1), cfg["vocab"], cfg["dim"]) for i in range(cfg["n_sparse"])]
+    cols += [DenseFeat("I%d" % (i + 1), 1) for i in range(cfg["n_dense"])]
+    return cols
+
+
+def synth_batches(cfg, n, rank=0):
+    """uniform ids (worst case for the gather: no reuse), U(0,1) dense, Bernoulli(0.25) labels; seed 2020."""
+    rng = np.random.RandomState(2020 + rank)
+    out = []
+    for _ in range(n):
+        ids = rng.randint(0, cfg["vocab"], size=(cfg["batch"], cfg["n_sparse"])).astype(np.int32)
+        dense = rng.rand(cfg["batch"], cfg["n_dense"]).astype(np.float32)
+        y = (rng.rand(cfg["batch"]) < 0.25).astype(np.float32)
+        out.append((ids, dense, y))
+    return out
+
+
+def as_inputs(cfg, ids, dense):
+    x = {"C%d" % (i + 1): ids[:, i] for i in range(cfg["n_sparse"])}
+    x.update({"I%d" % (i + 1): dense[:, i] for i in range(cfg["n_dense"])})
+    return x
+
+
+# ------------------------------------------------------------------------------------------------
+class ClockSampler(threading.Thread):
+    """nvidia-smi clocks + throttle reasons DURING the timed region (B200_PROFILING.md recipe)."""
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index=0):
+        threading.Thread.__init__(self, daemon=True)
+        self.index, self.rows, self.stop_flag = index, [], False
+
+    def run(self):
+        while not self.stop_flag:
+            try:
+                r = subprocess.run(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
+                                    "--format=csv,noheader,nounits"], capture_output=True, text=True, timeout=5)
+                if r.returncode == 0 and r.stdout.strip():
+                    self.rows.append([c.strip() for c in r.stdout.strip().split(",")])
+            except Exception:
+                pass
+            time.sleep(0.1)
+
+    def summary(self):
+        if not self.rows:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        sm = sorted(float(r[0]) for r in self.rows if r[0].replace(".", "").isdigit())
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = [n for i, n in enumerate(names) if any(len(r) > 3 + i and r[3 + i].lower().startswith("active")
+                                                         for r in self.rows)]
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None,
+                "sm_max_mhz": float(self.rows[0][1]) if self.rows[0][1].replace(".", "").isdigit() else None,
+                "reasons": reasons, "samples": len(self.rows)}
+
+
+def measured_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        d = json.load(open(p))
+        return {"hbm_gbs": d["hbm_gbs"], "bf16_tflops": d["bf16_tflops"],
+                "bf16_tflops_sustained": d.get("bf16_tflops_sustained", d["bf16_tflops"]), "which": "measured"}
+    return {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0, "bf16_tflops_sustained": 1400.0, "which": "fallback"}
+
+
+# ------------------------------------------------------------------------------------------------
+def cpu_step_factory(cfg, threads):
+    """The reference math (oracle/) as one DeepFM SGD step on host cores: fwd + BCE + autograd bwd +
+    row-wise SGD on the gathered rows (the reference's dense-Adam-over-tables semantics, SURVEY.md
+    App. C, cannot run at this table size on any hardware)."""
+    import torch
+    from oracle import ops as O
+    torch.set_num_threads(threads)
+    g = torch.Generator().manual_seed(1024)
+    F, E, nd, V = cfg["n_sparse"], cfg["dim"], cfg["n_dense"], cfg["vocab"]
+    tables = [torch.randn(V, E, generator=g) * 1e-2 for _ in range(F)]
+    lin = [torch.zeros(V, 1) for _ in range(F)]
+    dims = [F * E + nd] + list(cfg["hidden"])
+    ks = [(torch.randn(dims[i], dims[i + 1], generator=g) * (2.0 / (dims[i] + dims[i + 1])) ** 0.5).requires_grad_()
+          for i in range(len(dims) - 1)]
+    bs = [torch.zeros(d, requires_grad=True) for d in dims[1:]]
+    wd = (torch.randn(dims[-1], 1, generator=g) * 0.1).requires_grad_()
+    wl = (torch.randn(nd, 1, generator=g) * 0.1).requires_grad_()
+    gb = torch.zeros(1, requires_grad=True)
+    dense_params = ks + bs + [wd, wl, gb]
+
+    def step(ids, dense, y):
+        idx = torch.from_numpy(ids.astype(np.int64))
+        rows = [O.embedding_lookup(tables[f], idx[:, f]).detach().requires_grad_() for f in range(F)]
+        lrows = [O.embedding_lookup(lin[f], idx[:, f]).detach().requires_grad_() for f in range(F)]
+        x = torch.cat(rows, dim=1)
+        d = torch.from_numpy(dense)
+        logit = O.linear(torch.cat(lrows, dim=-1), d, wl) + O.fm(x)
+        h = O.dnn(torch.cat([x.flatten(1), d], dim=-1), ks, bs, "relu")
+        logit = logit + h @ wd
+        loss = O.binary_crossentropy(y, O.prediction(logit, gb, "binary"))
+        loss.backward()
+        with torch.no_grad():
+            for p in dense_params:
+                p -= LR * p.grad
+                p.grad = None
+            for f in range(F):
+                tables[f].index_add_(0, idx[:, f], rows[f].grad[:, 0, :], alpha=-LR)
+                lin[f].index_add_(0, idx[:, f], lrows[f].grad[:, 0, :], alpha=-LR)
+        return float(loss)
+
+    return step
+
+
+def run_cpu(cfg, steps, warmup, sample_batch):
+    threads = os.cpu_count() or 1
+    step = cpu_step_factory(cfg, threads)
+    small = dict(cfg, batch=sample_batch)
+    data = synth_batches(small, 2)
+    for i in range(warmup):
+        step(*data[i % 2])
+    t0 = time.perf_counter()
+    for i in range(steps):
+        step(*data[i % 2])
+    dt = time.perf_counter() - t0
+    return steps * sample_batch / dt, dt / steps * 1e3, threads
+
+
+# ------------------------------------------------------------------------------------------------
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="b2ctr", choices=["b2ctr", "reference"])
+    ap.add_argument("--config", default="c2", choices=sorted(CONFIGS))
+    ap.add_argument("--precision", default=os.environ.get("B2CTR_GEMM", "auto"))
+    ap.add_argument("--cpu-sample-batch", type=int, default=8192)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    cfg = CONFIGS[args.config]
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    warmup = max(args.warmup, 3)
+
+    if args.impl == "reference":
+        # the reference's own CPU path cannot run here (TensorFlow absent): the oracle port is timed
+        if rank != 0:
+            return
+        sb = min(args.cpu_sample_batch, cfg["batch"])
+        v, ms, threads = run_cpu(cfg, max(1, min(args.steps, 10)), min(warmup, 3), sb)
+        line = {"impl": "reference", "metric": "samples/sec fwd+bwd DeepFM Criteo-synth", "value": v,
+                "unit": "samples/s", "n_gpus": 0, "steps": min(args.steps, 10), "warmup": min(warmup, 3),
+                "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+                "dtype": "f32", "data": "synthetic",
+                "config": {"workload": cfg["workload"], "global_batch": sb, "optimizer": "sgd",
+                           "note": "oracle port (torch-CPU restatement of the reference math); TensorFlow is "
+                                   "not installable here; each step is a %d-sample slice of the batch" % sb},
+                "cpu_baseline": {"value": v, "unit": "samples/s", "cores": threads, "kind": "port",
+                                 "sample": "%d steps x %d samples of the c2 workload" % (min(args.steps, 10), sb)},
+                "e2e": {"value": v, "unit": "samples/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+        print(json.dumps(line))
+        return
+
+    import torch
+    import torch.distributed as dist
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device - the b2ctr path has no CPU fallback "
+                         "(use --impl reference for the CPU oracle)")
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    from deepctr_b200 import _lib as L, kernels as K, ops
+    from deepctr_b200.engine import SGD
+    from deepctr_b200.models import DeepFM
+
+    precision = args.precision
+    if precision == "auto":
+        precision = "fp32"
+    ops.set_gemm_precision(precision)
+    cols = feature_columns(cfg)
+    model = DeepFM(cols, cols, dnn_hidden_units=cfg["hidden"], l2_reg_linear=0, l2_reg_embedding=0, l2_reg_dnn=0)
+    model.compile(SGD(LR), "binary_crossentropy", embedding_update="sparse")
+    host = synth_batches(cfg, N_BATCHES, rank)
+    dev = torch.device("cuda", local_rank)
+    dev_batches = []
+    for ids, dense, y in host:
+        ids_d, dense_d, y_d = torch.from_numpy(ids).to(dev), torch.from_numpy(dense).to(dev), torch.from_numpy(y).to(dev)
+        x = {"C%d" % (i + 1): ids_d[:, i:i + 1] for i in range(cfg["n_sparse"])}
+        x["__dense__"] = dense_d
+        dev_batches.append((x, ids_d, dense_d, y_d))
+
+    def dev_inputs(b):
+        _, ids_d, dense_d, y_d = dev_batches[b]
+        x = {"C%d" % (i + 1): ids_d[:, i:i + 1] for i in range(cfg["n_sparse"])}
+        x.update({"I%d" % (i + 1): dense_d[:, i:i + 1] for i in range(cfg["n_dense"])})
+        return x, y_d
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # ---- device-resident timing ------------------------------------------------------------------
+    for i in range(warmup):
+        x, y = dev_inputs(i % N_BATCHES)
+        model.train_step(x, y)
+    barrier()
+    K.PROFILE = {}
+    L.reset_launch_count()
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    e0.record()
+    for i in range(args.steps):
+        x, y = dev_inputs(i % N_BATCHES)
+        model.train_step(x, y)
+    e1.record()
+    barrier()
+    launches = L.launch_count()
+    sampler.stop_flag = True
+    ms = e0.elapsed_time(e1)
+    prof = K.profile_summary()
+    K.PROFILE = None
+    t = torch.tensor([ms], device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms = float(t.item())
+    ms_per_step = ms / args.steps
+    value = world * cfg["batch"] * args.steps / (ms / 1e3)
+
+    # ---- end-to-end through the public API: host arrays in, loss out -------------------------------
+    model._feeder.h2d_bytes = 0
+    for i in range(3):
+        ids, dense, y = host[i % N_BATCHES]
+        model.train_on_batch(as_inputs(cfg, ids, dense), y)
+    model._feeder.h2d_bytes = 0
+    barrier()
+    t0 = time.perf_counter()
+    e0.record()
+    for i in range(args.steps):
+        ids, dense, y = host[i % N_BATCHES]
+        model.train_on_batch(as_inputs(cfg, ids, dense), y)     # returns the float loss (D2H + sync)
+    e1.record()
+    barrier()
+    e2e_ms = e0.elapsed_time(e1)
+    t = torch.tensor([e2e_ms], device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    e2e_ms = float(t.item())
+    e2e_value = world * cfg["batch"] * args.steps / (e2e_ms / 1e3)
+    h2d = model._feeder.h2d_bytes // args.steps
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
+    peaks = measured_peaks()
+    F, E, nd, B = cfg["n_sparse"], cfg["dim"], cfg["n_dense"], cfg["batch"]
+    # algorithmic bytes per sample
+    gather_fwd_bytes = F * 4 + F * E * 4 + F * E * 4 + F * 4 + 2 * nd * 4
+    scatter_bwd_bytes = F * 4 + F * E * 4 + F * E * 4 + 2 * F * E * 4 + 2 * F * 4
+    dims = [F * E + nd] + list(cfg["hidden"]) + [1]
+    kernels = {}
+    for name, (count, total_ms) in prof.items():
+        kernels[name] = {"launches": count, "ms_per_step": total_ms / args.steps}
+    def frac_hbm(name, bytes_per_sample):
+        if name not in prof or prof[name][0] == 0:
+            return None
+        avg_ms = prof[name][1] / prof[name][0]
+        a = bytes_per_sample * B / (avg_ms * 1e-3) / 1e9
+        return {"bound": "hbm", "achieved": a, "peak": peaks["hbm_gbs"], "unit": "GB/s",
+                "frac": a / peaks["hbm_gbs"], "traffic": None, "kernel": name,
+                "avg_launch_ms": avg_ms, "peak_source": peaks["which"],
+                "algorithmic_bytes_per_launch": bytes_per_sample * B}
+    roof_gather = frac_hbm("embed_gather_uniform_fwd", gather_fwd_bytes)
+    roof_scatter = frac_hbm("embed_scatter_uniform_bwd", scatter_bwd_bytes)
+    gemm_ms = sum(v[1] for k, v in prof.items() if k.startswith("gemm"))
+    gemm_flops = 3 * 2 * sum(dims[i] * dims[i + 1] for i in range(len(dims) - 1)) * B * args.steps
+    roof_gemm = None
+    if gemm_ms > 0:
+        a = gemm_flops / (gemm_ms * 1e-3) / 1e12
+        roof_gemm = {"bound": "tensor", "achieved": a, "peak": peaks["bf16_tflops_sustained"], "unit": "TFLOP/s",
+                     "frac": a / peaks["bf16_tflops_sustained"], "traffic": None, "kernel": "gemm (%s)" % precision,
+                     "peak_source": peaks["which"] + " (dense bf16, sustained)"}
+    cands = [r for r in (roof_gather, roof_scatter) if r is not None]
+    shares = {"gather+scatter_ms": sum(prof.get(k, (0, 0))[1] for k in ("embed_gather_uniform_fwd",
+                                                                       "embed_scatter_uniform_bwd")) / args.steps,
+              "gemm_ms": gemm_ms / args.steps, "step_ms": ms_per_step}
+    dominant = roof_gemm if (roof_gemm is not None and gemm_ms / args.steps > shares["gather+scatter_ms"]) else \
+        (max(cands, key=lambda r: r["avg_launch_ms"]) if cands else None)
+
+    cpu = None
+    if not args.no_cpu_baseline:
+        sb = min(args.cpu_sample_batch, cfg["batch"])
+        v, cms, threads = run_cpu(cfg, 4, 1, sb)
+        cpu = {"value": v, "unit": "samples/s", "cores": threads, "kind": "port",
+               "sample": "4 steps x %d samples of the same workload (oracle port, torch-CPU)" % sb}
+
+    line = {"metric": "samples/sec fwd+bwd DeepFM Criteo-synth", "value": value, "unit": "samples/s",
+            "n_gpus": world, "steps": args.steps, "warmup": warmup, "ms_per_step": ms_per_step,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
+            "data": "synthetic",
+            "config": {"workload": cfg["workload"], "global_batch": world * B, "optimizer": "sgd (fused row-wise)",
+                       "gemm_precision": precision, "parallelism": "replicas x%d" % world if world > 1 else "1 gpu",
+                       "l2_flush": "none: %d distinct batches cycle; per step the path touches %.1f GB of "
+                                   "randomly addressed table rows + activations, >> 126 MB L2"
+                                   % (N_BATCHES, (gather_fwd_bytes + scatter_bwd_bytes) * B / 1e9)},
+            "e2e": {"value": e2e_value, "unit": "samples/s", "h2d_bytes_per_step": int(h2d),
+                    "d2h_bytes_per_step": 4, "ms_per_step": e2e_ms / args.steps},
+            "gpu_launches": int(launches), "clocks": sampler.summary(),
+            "roofline": dominant, "roofline_gather_fwd": roof_gather, "roofline_scatter_bwd": roof_scatter,
+            "roofline_gemm": roof_gemm, "kernel_ms_per_step": kernels, "shares": shares,
+            "cpu_baseline": cpu}
+    print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -44,7 +44,8 @@ class UniformGather(C.Structure):
     """b2ctr_uniform_gather_t"""
     _fields_ = [("feats", C.POINTER(Feature)), ("lin_tables", C.POINTER(C.c_void_p)),
                 ("dense", C.c_void_p), ("x", C.c_void_p), ("linear", C.c_void_p), ("fm", C.c_void_p),
-                ("ldx", C.c_int64), ("dense_ld", C.c_int64), ("nfeat", C.c_int32),
+                ("ldx", C.c_int64), ("dense_ld", C.c_int64), ("x_cols", C.c_int64),
+                ("nfeat", C.c_int32),
                 ("ndense", C.c_int32), ("fm_mask", C.c_uint64 * 2)]
 
 
@@ -83,6 +84,8 @@ SIGNATURES = {
     "b2ctr_copy2d": (_i32, [_vp, _i64, _vp, _i64, _i64, _i64, _i32, _vp]),
     "b2ctr_rowsum": (_i32, [_vp, _i64, _vp, _i64, _i64, _vp]),
     "b2ctr_fill": (_i32, [_vp, _f32, _i64, _vp]),
+    "b2ctr_mask_nonzero_and": (_i32, [_vp, _i32, _i64, _vp, _i32, _vp]),
+    "b2ctr_mask_from_len": (_i32, [_vp, _i64, _i32, _vp, _vp]),
     "b2ctr_fm_fwd": (_i32, [_vp, _i64, _i32, _i32, _vp, _i64, _vp]),
     "b2ctr_fm_bwd": (_i32, [_vp, _i64, _i32, _i32, _vp, _vp, _i64, _i32, _i64, _vp]),
     "b2ctr_predict_loss": (_i32, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _i64, _i32, _vp]),

@@ -87,6 +87,19 @@ __global__ void copy2d_kernel(const float* __restrict__ src, int64_t lds, float*
     }
   }
 }
+__global__ void mask_nonzero_and_kernel(const void* ids, int dtype, int64_t n, uint8_t* io, int first) {
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n;
+       i += (int64_t)gridDim.x * blockDim.x) {
+    const uint8_t v = load_idx(ids, i, dtype) != 0;
+    io[i] = first ? v : (uint8_t)(io[i] & v);
+  }
+}
+__global__ void mask_from_len_kernel(const int32_t* len, int64_t batch, int maxlen, uint8_t* out) {
+  const int64_t n = batch * maxlen;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n;
+       i += (int64_t)gridDim.x * blockDim.x)
+    out[i] = (int)(i % maxlen) < len[i / maxlen];
+}
 // one warp per row, lanes stride the columns; partials combined in a fixed shuffle tree
 __global__ void rowsum_kernel(const float* __restrict__ x, int64_t ld, float* out, int64_t rows,
                               int64_t cols) {
@@ -302,6 +315,25 @@ b2ctr_status_t b2ctr_fill(float* dst, float value, int64_t n, void* stream) {
   if (n <= 0) return B2CTR_OK;
   fill_kernel<<<grid_for(n, 256, 8), 256, 0, ST>>>(dst, value, n);
   B2_CHECK_LAUNCH("b2ctr_fill");
+  return B2CTR_OK;
+}
+
+b2ctr_status_t b2ctr_mask_nonzero_and(const void* ids, int32_t idx_dtype, int64_t n, uint8_t* inout,
+                                      int32_t first, void* stream) {
+  B2_REQUIRE(ids && inout, "mask_nonzero_and: NULL pointer");
+  B2_REQUIRE(idx_dtype == B2CTR_IDX_I32 || idx_dtype == B2CTR_IDX_I64, "mask_nonzero_and: bad dtype");
+  if (n <= 0) return B2CTR_OK;
+  mask_nonzero_and_kernel<<<grid_for(n, 256, 8), 256, 0, ST>>>(ids, idx_dtype, n, inout, first);
+  B2_CHECK_LAUNCH("b2ctr_mask_nonzero_and");
+  return B2CTR_OK;
+}
+
+b2ctr_status_t b2ctr_mask_from_len(const int32_t* len, int64_t batch, int32_t maxlen, uint8_t* out,
+                                   void* stream) {
+  B2_REQUIRE(len && out && maxlen > 0, "mask_from_len: bad arguments");
+  if (batch <= 0) return B2CTR_OK;
+  mask_from_len_kernel<<<grid_for(batch * maxlen, 256, 8), 256, 0, ST>>>(len, batch, maxlen, out);
+  B2_CHECK_LAUNCH("b2ctr_mask_from_len");
   return B2CTR_OK;
 }
 

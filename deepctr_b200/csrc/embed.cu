@@ -381,6 +381,7 @@ struct UniParams {
   float* fm;
   int64_t ldx;
   int64_t dense_ld;
+  int64_t x_cols;
   uint64_t fm_mask;
   int32_t nfeat;
   int32_t ndense;
@@ -461,7 +462,7 @@ __global__ void __launch_bounds__(256)
     }
     // dense passthrough + zero padding up to ldx (so x is directly the K-padded GEMM operand)
     const int64_t c0 = (int64_t)F * dim;
-    for (int64_t c = c0 + lane; c < p.ldx; c += 32) {
+    for (int64_t c = c0 + lane; c < p.x_cols; c += 32) {
       const int j = (int)(c - c0);
       xrow[c] = j < p.ndense ? p.dense[b * p.dense_ld + j] : 0.f;
     }
@@ -676,6 +677,8 @@ static b2ctr_status_t fill_uni(const b2ctr_uniform_gather_t* g, UniParams* p) {
   p->fm = g->fm;
   p->ldx = g->ldx;
   p->dense_ld = g->dense_ld;
+  p->x_cols = g->x_cols > 0 ? g->x_cols : g->ldx;
+  B2_REQUIRE(p->x_cols <= g->ldx && p->x_cols >= (int64_t)g->nfeat * dim + g->ndense, "uniform gather: x_cols out of range");
   p->fm_mask = g->fm_mask[0];
   p->nfeat = g->nfeat;
   p->ndense = g->ndense;

@@ -1,0 +1,822 @@
+"""Host mirror of deepctr/inputs.py plus the machinery that turns its per-feature ``Embedding``
+calls into ONE fused launch per step.
+
+Reference functions mirrored (same names / arguments / return structure):
+``create_embedding_dict`` (inputs.py:44-71), ``create_embedding_matrix`` (:89-98),
+``embedding_lookup`` (:101-117), ``varlen_embedding_lookup`` (:120-130),
+``get_varlen_pooling_list`` (:133-158), ``get_dense_input`` (:161-172), ``mergeDict`` (:175-181),
+``get_embedding_vec_list`` (:74-86), ``get_inputs_list`` (:40-41).
+
+B200 design: the builders still call ``Embedding`` once per feature, but the
+``EmbeddingPlanner`` owned by the Model recognises, once per graph, every lookup whose ids are a
+model input (optionally through ``Hash``) and every ``SequencePoolingLayer`` /
+``WeightedSequenceLayer`` chain hanging off such a lookup, lays all their outputs out as adjacent
+column windows of one [B, ld] buffer, and serves them from a single kernel launch
+(``b2ctr_embed_gather_uniform_fwd`` for the Criteo shape, ``b2ctr_embed_gather_fwd`` otherwise).
+Concatenations of those windows are then zero-copy views, and the backward pass is a single fused
+scatter (+ SGD update) launch.
+"""
+from collections import defaultdict, OrderedDict
+from itertools import chain
+
+import numpy as np
+import torch
+
+from . import _lib as L
+from . import kernels as K
+from . import engine as E
+from .engine import Layer, l2
+
+
+# ================================================================================================
+# Embedding layer (tf.keras.layers.Embedding surface used by deepctr/inputs.py:19-26)
+# ================================================================================================
+class Embedding(Layer):
+    def __init__(self, input_dim, output_dim, embeddings_initializer=None, embeddings_regularizer=None,
+                 mask_zero=False, name=None, **kwargs):
+        Layer.__init__(self, name=name, **kwargs)
+        self.input_dim, self.output_dim = int(input_dim), int(output_dim)
+        self.embeddings_initializer = embeddings_initializer or E.RandomNormal(0.0, 0.05)
+        self.embeddings_regularizer = embeddings_regularizer
+        self.mask_zero = mask_zero
+        self.supports_masking = mask_zero
+        # tables are created eagerly so that they exist (and can be set) before any call
+        self.embeddings = self.add_weight("embeddings", (self.input_dim, self.output_dim),
+                                          self.embeddings_initializer, self.embeddings_regularizer,
+                                          trainable=self.trainable)
+        self.built = True
+
+    def _output_dtype(self, inputs):
+        return "float32"
+
+    def compute_output_shape(self, input_shape):
+        return tuple(input_shape) + (self.output_dim,)
+
+    def compute_mask(self, inputs, mask=None):
+        if not self.mask_zero:
+            return None
+        return E.KMask(ids=[inputs.data])
+
+    def call(self, inputs, **kwargs):
+        """Unplanned (eager / computed ids) lookup: one generic-kernel launch for this table."""
+        ids = inputs.data
+        if ids.dtype not in (torch.int32, torch.int64):
+            ids = ids.to(torch.int64)
+        ids2 = ids.reshape(ids.shape[0], -1).contiguous()
+        b, t = ids2.shape
+        table = self.embeddings.materialize()
+        out = torch.empty((b, t * self.output_dim), dtype=torch.float32, device=ids.device)
+        feat = K.make_feature(table, ids2, out, maxlen=t)
+        K.embed_gather_fwd([feat], b)
+        res = E.Var(out.reshape(tuple(ids.shape) + (self.output_dim,)))
+        w = self.embeddings
+
+        def bwd(grads):
+            g = grads[0].reshape(b, t * self.output_dim).contiguous()
+            tgt, scale = _grad_target(w, E.current_opt())
+            fb = K.make_feature(tgt, ids2, g, maxlen=t)
+            K.embed_scatter_add([fb], b, scale)
+
+        E.record([res], [w], bwd)
+        return res
+
+    def get_config(self):
+        c = Layer.get_config(self)
+        c.update(input_dim=self.input_dim, output_dim=self.output_dim, mask_zero=self.mask_zero)
+        return c
+
+
+def _grad_target(w, opt_ctx):
+    """Where a table gradient goes: the table itself (fused SGD, scale=-lr) or a dense .grad buffer."""
+    if w.sparse_grad:
+        lr = opt_ctx["optimizer"].lr if opt_ctx and opt_ctx.get("optimizer") else 0.0
+        return w.data, -lr
+    if w.grad is None:
+        w.grad = torch.empty_like(w.data)
+        K.fill(w.grad, 0.0)
+    return w.grad, 1.0
+
+
+# ================================================================================================
+# reference-compatible functions
+# ================================================================================================
+def _create_embedding_layer(feat, l2_reg, prefix, name_suffix, mask_zero=False):
+    """deepctr/inputs.py:19-26."""
+    emb = Embedding(feat.vocabulary_size, feat.embedding_dim,
+                    embeddings_initializer=feat.embeddings_initializer,
+                    embeddings_regularizer=l2(l2_reg),
+                    name=prefix + '_' + name_suffix + '_' + feat.embedding_name,
+                    mask_zero=mask_zero, trainable=feat.trainable)
+    return emb
+
+
+def _check_embedding_compatible(embedding_name, existing_feat, feat):
+    """deepctr/inputs.py:29-37 (same message)."""
+    for attr in ('vocabulary_size', 'embedding_dim', 'trainable'):
+        if getattr(existing_feat, attr) != getattr(feat, attr):
+            raise ValueError(
+                "Feature columns with the same embedding_name must share the same "
+                "{}. embedding_name='{}' has {} and {}.".format(
+                    attr, embedding_name, getattr(existing_feat, attr), getattr(feat, attr)))
+
+
+def get_inputs_list(inputs):
+    return list(chain(*list(map(lambda x: x.values(), filter(lambda x: x is not None, inputs)))))
+
+
+def create_embedding_dict(sparse_feature_columns, varlen_sparse_feature_columns, seed, l2_reg,
+                          prefix='sparse_', seq_mask_zero=True):
+    """deepctr/inputs.py:44-71: one table per distinct embedding_name; mask_zero when shared with /
+    owned by a VarLen column."""
+    sparse_embedding = {}
+    embedding_feature_dict = {}
+    varlen_names = set(f.embedding_name for f in varlen_sparse_feature_columns) \
+        if varlen_sparse_feature_columns else set()
+    for feat in sparse_feature_columns:
+        name = feat.embedding_name
+        if name in sparse_embedding:
+            _check_embedding_compatible(name, embedding_feature_dict[name], feat)
+            continue
+        mask_zero = seq_mask_zero and name in varlen_names
+        sparse_embedding[name] = _create_embedding_layer(feat, l2_reg, prefix, 'emb', mask_zero)
+        embedding_feature_dict[name] = feat
+    if varlen_sparse_feature_columns:
+        for feat in varlen_sparse_feature_columns:
+            name = feat.embedding_name
+            if name in sparse_embedding:
+                _check_embedding_compatible(name, embedding_feature_dict[name], feat)
+                continue
+            sparse_embedding[name] = _create_embedding_layer(feat, l2_reg, prefix, 'seq_emb', seq_mask_zero)
+            embedding_feature_dict[name] = feat
+    return sparse_embedding
+
+
+def create_embedding_matrix(feature_columns, l2_reg, seed, prefix="", seq_mask_zero=True):
+    from . import feature_column as fc_lib
+    sparse = [x for x in feature_columns if isinstance(x, fc_lib.SparseFeat)] if feature_columns else []
+    varlen = [x for x in feature_columns if isinstance(x, fc_lib.VarLenSparseFeat)] if feature_columns else []
+    return create_embedding_dict(sparse, varlen, seed, l2_reg, prefix=prefix + 'sparse',
+                                 seq_mask_zero=seq_mask_zero)
+
+
+def _hash_layer(fc, mask_zero):
+    from .layers.utils import Hash
+    return Hash(fc.vocabulary_size, mask_zero=mask_zero, vocabulary_path=fc.vocabulary_path)
+
+
+def get_embedding_vec_list(embedding_dict, input_dict, sparse_feature_columns, return_feat_list=(),
+                           mask_feat_list=()):
+    vecs = []
+    for fg in sparse_feature_columns:
+        name = fg.name
+        if len(return_feat_list) == 0 or name in return_feat_list:
+            idx = _hash_layer(fg, name in mask_feat_list)(input_dict[name]) if fg.use_hash else input_dict[name]
+            vecs.append(embedding_dict[name](idx))
+    return vecs
+
+
+def embedding_lookup(sparse_embedding_dict, sparse_input_dict, sparse_feature_columns, return_feat_list=(),
+                     mask_feat_list=(), to_list=False):
+    """deepctr/inputs.py:101-117."""
+    group_embedding_dict = defaultdict(list)
+    for fc in sparse_feature_columns:
+        feature_name, embedding_name = fc.name, fc.embedding_name
+        if len(return_feat_list) == 0 or feature_name in return_feat_list:
+            if fc.use_hash:
+                lookup_idx = _hash_layer(fc, feature_name in mask_feat_list)(sparse_input_dict[feature_name])
+            else:
+                lookup_idx = sparse_input_dict[feature_name]
+            group_embedding_dict[fc.group_name].append(sparse_embedding_dict[embedding_name](lookup_idx))
+    if to_list:
+        return list(chain.from_iterable(group_embedding_dict.values()))
+    return group_embedding_dict
+
+
+def varlen_embedding_lookup(embedding_dict, sequence_input_dict, varlen_sparse_feature_columns):
+    """deepctr/inputs.py:120-130."""
+    out = {}
+    for fc in varlen_sparse_feature_columns:
+        if fc.use_hash:
+            lookup_idx = _hash_layer(fc, True)(sequence_input_dict[fc.name])
+        else:
+            lookup_idx = sequence_input_dict[fc.name]
+        out[fc.name] = embedding_dict[fc.embedding_name](lookup_idx)
+    return out
+
+
+def get_varlen_pooling_list(embedding_dict, features, varlen_sparse_feature_columns, to_list=False):
+    """deepctr/inputs.py:133-158."""
+    from .layers.sequence import SequencePoolingLayer, WeightedSequenceLayer
+    pooling_vec_list = defaultdict(list)
+    for fc in varlen_sparse_feature_columns:
+        name, combiner, length_name = fc.name, fc.combiner, fc.length_name
+        if length_name is not None:
+            if fc.weight_name is not None:
+                seq_input = WeightedSequenceLayer(weight_normalization=fc.weight_norm)(
+                    [embedding_dict[name], features[length_name], features[fc.weight_name]])
+            else:
+                seq_input = embedding_dict[name]
+            vec = SequencePoolingLayer(combiner, supports_masking=False)([seq_input, features[length_name]])
+        else:
+            if fc.weight_name is not None:
+                seq_input = WeightedSequenceLayer(weight_normalization=fc.weight_norm, supports_masking=True)(
+                    [embedding_dict[name], features[fc.weight_name]])
+            else:
+                seq_input = embedding_dict[name]
+            vec = SequencePoolingLayer(combiner, supports_masking=True)(seq_input)
+        pooling_vec_list[fc.group_name].append(vec)
+    if to_list:
+        return chain.from_iterable(pooling_vec_list.values())
+    return pooling_vec_list
+
+
+def get_dense_input(features, feature_columns):
+    """deepctr/inputs.py:161-172."""
+    from . import feature_column as fc_lib
+    dense_cols = [x for x in feature_columns if isinstance(x, fc_lib.DenseFeat)] if feature_columns else []
+    out = []
+    for fc in dense_cols:
+        if fc.transform_fn is None:
+            out.append(features[fc.name])
+        else:
+            out.append(E.Lambda(fc.transform_fn)(features[fc.name]))
+    return out
+
+
+def mergeDict(a, b):
+    c = defaultdict(list)
+    for k, v in a.items():
+        c[k].extend(v)
+    for k, v in b.items():
+        c[k].extend(v)
+    return c
+
+
+# ================================================================================================
+# EmbeddingPlanner: graph pattern -> one fused launch
+# ================================================================================================
+VIRTUAL = object()   # result of a node folded into a fused descriptor (never consumed)
+
+
+class _Slot(object):
+    """One planned output: a lookup (single / sequence) or a pooled bag."""
+    __slots__ = ("node", "emb", "input_name", "hash", "maxlen", "pool", "mask_mode", "len_name",
+                 "weight_name", "weight_mode", "dim", "col", "buf", "out_shape", "virtual_nodes",
+                 "mask_zero")
+
+
+class EmbeddingPlanner(object):
+    def __init__(self, model):
+        from .layers.utils import Hash
+        from .layers.sequence import SequencePoolingLayer, WeightedSequenceLayer
+        self.model = model
+        self.slots = []
+        self.results = {}
+        self.optimizer = None
+        self.mode = "auto"
+        self.fm_hint = None        # (col0, ncols) of the main buffer an FM layer consumed
+        self.lin_hint = False      # the linear buffer is only ever row-summed
+        self.tail_hint = None      # (dense col0, ncols) appended behind the main buffer
+        self.fm_result = None
+        self.lin_result = None
+        self._plans = {}
+        consumers = defaultdict(list)
+        for node in model._order:
+            for t in E._flatten(node.inputs):
+                consumers[id(t)].append(node)
+        out_ids = set(id(t) for t in E._flatten(model.outputs))
+        input_names = set(t.name for t in model.inputs)
+
+        def as_input(t):
+            return t.name if (isinstance(t.node.layer, E.InputLayer) and t.name in input_names) else None
+
+        for node in model._order:
+            if not isinstance(node.layer, Embedding) or not isinstance(node.inputs, E.KTensor):
+                continue
+            src, hcfg, virt = node.inputs, None, []
+            if isinstance(src.node.layer, Hash) and isinstance(src.node.inputs, E.KTensor):
+                h = src.node.layer
+                if len(consumers[id(src)]) == 1 and id(src) not in out_ids:
+                    hcfg, virt, src = h, [src.node], src.node.inputs
+            name = as_input(src)
+            if name is None:
+                continue
+            if hcfg is not None and (hcfg.vocabulary_path or src.dtype in ("string", str)):
+                hash_mode, prehashed = L.HASH_NONE, hcfg      # resolved on the host by the Feeder
+            elif hcfg is not None:
+                hash_mode, prehashed = (L.HASH_FARM_MASK_ZERO if hcfg.mask_zero else L.HASH_FARM), None
+            else:
+                hash_mode, prehashed = L.HASH_NONE, None
+            s = _Slot()
+            s.emb, s.input_name, s.hash = node.layer, name, (hash_mode, prehashed)
+            s.maxlen = int(np.prod(src.shape[1:])) if len(src.shape) > 1 else 1
+            s.dim, s.mask_zero = node.layer.output_dim, node.layer.mask_zero
+            s.pool, s.mask_mode, s.len_name, s.weight_name, s.weight_mode = L.POOL_NONE, L.MASK_NONE, None, None, L.WEIGHT_NONE
+            s.node, s.virtual_nodes = node, list(virt)
+            out_t = node.outputs[0]
+            cons = consumers[id(out_t)]
+            # --- pooled-bag patterns of get_varlen_pooling_list (inputs.py:133-158) ----------------
+            if len(cons) == 1 and id(out_t) not in out_ids:
+                c = cons[0]
+                wnode = None
+                if isinstance(c.layer, WeightedSequenceLayer) and E._flatten(c.inputs)[0] is out_t:
+                    wins = E._flatten(c.inputs)
+                    wt = c.outputs[0]
+                    wc = consumers[id(wt)]
+                    if (len(wc) == 1 and id(wt) not in out_ids and isinstance(wc[0].layer, SequencePoolingLayer)
+                            and all(as_input(t) for t in wins[1:])):
+                        wnode, c = c, wc[0]
+                if isinstance(c.layer, SequencePoolingLayer):
+                    pins = E._flatten(c.inputs)
+                    first = wnode.outputs[0] if wnode is not None else out_t
+                    ok = pins[0] is first and all(as_input(t) for t in pins[1:])
+                    pl = c.layer
+                    if ok and pl.supports_masking and not s.mask_zero:
+                        ok = False   # reference raises at run time: input must carry a mask
+                    if ok and wnode is not None and wnode.layer.supports_masking != pl.supports_masking:
+                        ok = False
+                    if ok:
+                        s.pool = L.POOL_BY_NAME[pl.mode]
+                        if pl.supports_masking:
+                            s.mask_mode = L.MASK_ZERO_ID
+                        else:
+                            s.mask_mode, s.len_name = L.MASK_LENGTH, pins[1].name
+                        if wnode is not None:
+                            wins = E._flatten(wnode.inputs)
+                            s.weight_name = wins[-1].name
+                            s.weight_mode = L.WEIGHT_SOFTMAX if wnode.layer.weight_normalization else L.WEIGHT_RAW
+                            s.virtual_nodes.append(wnode)
+                        s.virtual_nodes.append(node)
+                        s.node = c
+            self.slots.append(s)
+        # ---- column layout: dim-1 lookups (linear terms) | everything else | sequences ------------
+        self.main = [s for s in self.slots if not (s.pool == L.POOL_NONE and s.maxlen > 1) and s.dim > 1]
+        self.lin = [s for s in self.slots if not (s.pool == L.POOL_NONE and s.maxlen > 1) and s.dim == 1]
+        self.seq = [s for s in self.slots if s.pool == L.POOL_NONE and s.maxlen > 1]
+        for group, tag in ((self.main, "main"), (self.lin, "lin")):
+            col = 0
+            for s in group:
+                s.buf, s.col = tag, col
+                col += s.dim
+        self.main_width = sum(s.dim for s in self.main)
+        self.lin_width = sum(s.dim for s in self.lin)
+        for s in self.seq:
+            s.buf, s.col = "seq", 0
+        self.tail_reserve = 0
+        for t in model.inputs:
+            if t.dtype in ("float32", "float64", "float16") and len(t.shape) == 2:
+                self.tail_reserve += int(t.shape[1])
+        self.main_ld = (self.main_width + self.tail_reserve + 3) // 4 * 4
+        self.lin_ld = max(1, (self.lin_width + 3) // 4 * 4)
+        self.fast = self._fast_eligible()
+
+    # ---- configuration ---------------------------------------------------------------------------
+    def tables(self):
+        seen, out = set(), []
+        for s in self.slots:
+            if id(s.emb.embeddings) not in seen:
+                seen.add(id(s.emb.embeddings))
+                out.append(s.emb.embeddings)
+        return out
+
+    def configure(self, optimizer, mode):
+        self.optimizer, self.mode = optimizer, mode
+        total = sum(w.numel() for w in self.tables())
+        sparse = mode == "sparse" or (mode == "auto" and total > (1 << 22))
+        if sparse and optimizer.name != "sgd":
+            raise ValueError("embedding_update='sparse' (tables too large for dense updates) supports the "
+                             "'sgd' optimizer only; got %r" % optimizer.name)
+        for w in self.tables():
+            w.sparse_grad = bool(sparse and w.trainable)
+        # unplanned Embedding layers follow the same policy
+        for l in self.model.layers:
+            if isinstance(l, Embedding):
+                l.embeddings.sparse_grad = bool(sparse and l.embeddings.trainable)
+
+    def _fast_eligible(self):
+        m = self.main
+        if not m or len(m) > 64:
+            return False
+        d = m[0].dim
+        if d not in (4, 8, 16, 32, 64, 128):
+            return False
+        # the leading run of plain single-valued features (rest of `main` goes through the generic kernel)
+        n = 0
+        for s in m:
+            if s.dim == d and s.maxlen == 1 and s.pool == L.POOL_NONE and s.hash[0] == L.HASH_NONE:
+                n += 1
+            else:
+                break
+        self.fast_n = n
+        return n >= 1
+
+    def _lin_matches_fast(self):
+        """linear (dim-1) lookups mirror the fast features one-to-one -> summed inside the kernel."""
+        if not self.lin or len(self.lin) != self.fast_n or len(self.main) != self.fast_n:
+            return False
+        for a, b in zip(self.lin, self.main):
+            if (a.input_name != b.input_name or a.maxlen != 1 or a.pool != L.POOL_NONE
+                    or a.hash[0] != L.HASH_NONE):
+                return False
+        return True
+
+    # ---- per-step execution ------------------------------------------------------------------------
+    def begin_step(self, feed, training):
+        self.results = {}
+        self.fm_result = self.lin_result = None
+        self.tail_done = None
+        if not self.slots:
+            return
+        some = feed[self.slots[0].input_name].data
+        batch, dev = some.shape[0], some.device
+        grad = training and E.current_tape() is not None
+        bufs = {}
+        if self.main:
+            bufs["main"] = E.Var(torch.empty((batch, self.main_ld), dtype=torch.float32, device=dev),
+                                 ncols=self.main_width, owner=self)
+        lin_fused = self.fast and self.lin_hint and self._lin_matches_fast()
+        if self.lin and not lin_fused:
+            bufs["lin"] = E.Var(torch.empty((batch, self.lin_ld), dtype=torch.float32, device=dev),
+                                ncols=self.lin_width, owner=self)
+        generic = []
+        for s in self.slots:
+            if s.buf == "seq":
+                bufs[id(s)] = E.Var(torch.empty((batch, s.maxlen * s.dim), dtype=torch.float32, device=dev),
+                                    owner=self)
+        fast_slots = self.main[:self.fast_n] if self.fast else []
+        for s in self.slots:
+            if s in fast_slots or (lin_fused and s.buf == "lin"):
+                continue
+            generic.append(s)
+        tables_used = []
+        # ---- fast path launch -----------------------------------------------------------------------
+        plan = None
+        if fast_slots:
+            x = bufs["main"].data
+            feats = [self._feature(s, feed, x, self.main_ld) for s in fast_slots]
+            lin_tabs = [s.emb.embeddings.materialize().reshape(-1) for s in self.lin] if lin_fused else None
+            only_fast = len(self.main) == self.fast_n
+            dense = None
+            if only_fast and self.tail_hint is not None and "__dense_pack__" in feed:
+                c0, nd = self.tail_hint
+                dp = feed["__dense_pack__"].data
+                if c0 + nd <= dp.shape[1] and self.main_width + nd <= self.main_ld:
+                    dense = dp[:, c0:c0 + nd]
+                    self.tail_done = (c0, nd)
+            linear = torch.empty((batch,), dtype=torch.float32, device=dev) if lin_fused else None
+            fm, fm_mask = None, 0
+            if self.fm_hint is not None:
+                c0, nc = self.fm_hint
+                d = fast_slots[0].dim
+                if c0 % d == 0 and nc % d == 0 and c0 + nc <= self.fast_n * d:
+                    fm = torch.empty((batch,), dtype=torch.float32, device=dev)
+                    for f in range(c0 // d, (c0 + nc) // d):
+                        fm_mask |= 1 << f
+            plan = K.UniformPlan(feats, lin_tabs, dense, x, linear, fm, fm_mask)
+            plan.g.x_cols = self.main_ld if only_fast else self.fast_n * fast_slots[0].dim
+            K.embed_gather_uniform_fwd(plan, batch)
+            if fm is not None:
+                self.fm_result = (self.fm_hint, E.Var(fm.reshape(batch, 1)))
+            if linear is not None:
+                self.lin_result = E.Var(linear.reshape(batch, 1))
+        # ---- generic launch for everything else ------------------------------------------------------
+        if generic:
+            feats = []
+            for s in generic:
+                buf = bufs[id(s)] if s.buf == "seq" else bufs[s.buf]
+                feats.append(self._feature(s, feed, buf.data, buf.data.stride(0)))
+            K.embed_gather_fwd(feats, batch)
+        # ---- hand the windows to the graph executor ---------------------------------------------------
+        from . import ops
+        for s in self.slots:
+            if s.buf == "lin" and lin_fused:
+                base = E.Var(None, owner=self)       # virtual: only its row-sum exists this step
+                base.name = "__virtual_lin__"
+                out = E.Var(None, base=base, col0=s.col, ncols=s.dim, owner=self)
+            elif s.buf == "seq":
+                base = bufs[id(s)]
+                out = ops._window(base, 0, s.maxlen * s.dim, (batch, s.maxlen, s.dim))
+            else:
+                base = bufs[s.buf]
+                out = ops._window(base, s.col, s.dim, (batch, 1, s.dim))
+            if s.pool == L.POOL_NONE and s.mask_zero:
+                out.mask = E.KMask(ids=[feed[s.input_name].data], hashed=s.hash)
+            out.requires_grad = grad and s.emb.embeddings.trainable
+            self.results[id(s.node)] = out
+            for vn in s.virtual_nodes:
+                if vn is not s.node:
+                    self.results[id(vn)] = VIRTUAL
+        if grad:
+            outs = [b for b in bufs.values()]
+            if self.fm_result is not None:
+                outs.append(self.fm_result[1])
+            if self.lin_result is not None:
+                outs.append(self.lin_result)
+            for o in outs:
+                o.requires_grad = True
+            tape = E.current_tape()
+            tape.record(outs, lambda grads: self._backward(feed, bufs, plan, fast_slots, generic, lin_fused,
+                                                           batch))
+
+    def _feature(self, s, feed, out, out_ld, table=None, src_table=None):
+        ids = feed[s.input_name].data
+        length = feed[s.len_name].data if s.len_name else None
+        weight = feed[s.weight_name].data if s.weight_name else None
+        if length is not None and length.dtype != torch.int32:
+            raise ValueError("sequence lengths must be int32")
+        tab = table if table is not None else s.emb.embeddings.materialize()
+        return K.make_feature(tab, ids, out, out_col=s.col if s.buf != "seq" else 0, out_ld=out_ld,
+                              maxlen=s.maxlen, pool=s.pool, mask_mode=s.mask_mode, length=length,
+                              weight=weight, weight_mode=s.weight_mode, hash_mode=s.hash[0],
+                              src_table=src_table)
+
+    @staticmethod
+    def _target(w, opt):
+        """(buffer, scale) for a table in the fused scatter; frozen tables land in a scratch buffer."""
+        if not w.trainable:
+            scratch = w.opt_state.get("scratch")
+            if scratch is None:
+                scratch = w.opt_state["scratch"] = torch.empty_like(w.data)
+            return scratch, 0.0
+        return _grad_target(w, opt)
+
+    def _backward(self, feed, bufs, plan, fast_slots, generic, lin_fused, batch):
+        opt = E.current_opt()
+        if fast_slots:
+            main = bufs["main"]
+            dx = main.grad
+            dfm = self.fm_result[1].grad if self.fm_result is not None else None
+            dlin = self.lin_result.grad if self.lin_result is not None else None
+            if dx is not None or dfm is not None or dlin is not None:
+                tgts = [self._target(s.emb.embeddings, opt) for s in fast_slots]
+                feats = [self._feature(s, feed, main.data, self.main_ld, table=tgt)
+                         for s, (tgt, _) in zip(fast_slots, tgts)]
+                scale = max(abs(sc) for _, sc in tgts) * (-1.0 if any(sc < 0 for _, sc in tgts) else 1.0)
+                lin_tabs, lin_scale = None, 0.0
+                if lin_fused:
+                    lt = [self._target(s.emb.embeddings, opt) for s in self.lin]
+                    lin_tabs = [t.reshape(-1) for t, _ in lt]
+                    lin_scale = max(abs(sc) for _, sc in lt) * (-1.0 if any(sc < 0 for _, sc in lt) else 1.0)
+                bplan = K.UniformPlan(feats, lin_tabs, None, main.data, None, None, plan.g.fm_mask[0])
+                bplan.g.x_cols = plan.g.x_cols
+                K.embed_scatter_uniform_bwd(bplan, dx, None if dfm is None else dfm.reshape(-1).contiguous(),
+                                            None if dlin is None else dlin.reshape(-1).contiguous(),
+                                            scale, lin_scale, batch)
+        feats, scales = [], []
+        for s in generic:
+            if not s.emb.embeddings.trainable:
+                continue
+            buf = bufs[id(s)] if s.buf == "seq" else bufs[s.buf]
+            if buf.grad is None:
+                continue
+            tgt, scale = _grad_target(s.emb.embeddings, opt)
+            src = s.emb.embeddings.data if s.pool == L.POOL_MAX else None
+            feats.append(self._feature(s, feed, buf.grad, buf.grad.stride(0), table=tgt, src_table=src))
+            scales.append(scale)
+        # one launch per distinct scale (normally exactly one)
+        for sc in sorted(set(scales)):
+            K.embed_scatter_add([f for f, s_ in zip(feats, scales) if s_ == sc], batch, sc)
+
+    # ---- fusion hooks used by layers ---------------------------------------------------------------
+    def lookup_fm(self, x):
+        """FM layer: return the in-kernel FM if this step computed it for exactly this window."""
+        if x.base is None or x.base.owner is not self or x.ncols == -1:
+            return None
+        if x.base.ncols != self.main_width or x.base.data is None or x.base.data.shape[1] != self.main_ld:
+            return None
+        key = (x.col0, x.ncols)
+        if self.fm_result is not None and self.fm_result[0] == key:
+            return self.fm_result[1]
+        if self.fast:
+            self.fm_hint = key      # fused from the next step on
+        return None
+
+    def lookup_rowsum(self, x):
+        if x.base is None or x.base.owner is not self:
+            return None
+        if x.base.name == "__virtual_lin__":
+            if x.col0 == 0 and x.ncols == self.lin_width and self.lin_result is not None:
+                return self.lin_result
+            raise L.B2ctrError("the linear-term lookups were fused into a row-sum but a layer asked for the rows")
+        if (self.fast and x.base.ncols == self.lin_width and x.col0 == 0 and x.ncols == self.lin_width
+                and x.base.data.shape[1] == self.lin_ld and self._lin_matches_fast()):
+            self.lin_hint = True
+        return None
+
+    def append_dense(self, emb_flat, dense_flat):
+        """combined_dnn_input: place the dense features behind the embeddings in the main buffer so the
+        DNN input is a zero-copy window.  Returns the window or None."""
+        from . import ops
+        if (emb_flat.base is None or emb_flat.base.owner is not self or emb_flat.ncols == -1
+                or emb_flat.base.ncols != self.main_width or emb_flat.base.data is None
+                or emb_flat.base.data.shape[1] != self.main_ld):
+            return None
+        if emb_flat.col0 != 0 or emb_flat.ncols != self.main_width:
+            return None
+        b = emb_flat.data.shape[0]
+        nd = dense_flat.data.shape[1]
+        if self.main_width + nd > self.main_ld:
+            return None
+        base = emb_flat.base
+        is_pack = (dense_flat.base is not None and dense_flat.base.name == "__dense_pack__"
+                   and dense_flat.ncols != -1)
+        if is_pack and self.tail_done == (dense_flat.col0, nd):
+            pass    # the gather kernel already wrote it
+        else:
+            src, ld = dense_flat.flat2d()
+            if src is None:
+                return None
+            K.copy2d(src, ld, base.data, base.data.stride(0), b, nd, dst_off=self.main_width)
+            if is_pack and self.fast and len(self.main) == self.fast_n:
+                self.tail_hint = (dense_flat.col0, nd)
+        return ops._window(base, 0, self.main_width + nd, (b, self.main_width + nd))
+
+
+# ================================================================================================
+# Feeder: host arrays -> few packed, pinned H2D copies -> Vars
+# ================================================================================================
+def slice_inputs(x, sl):
+    if isinstance(x, dict):
+        return {k: _take(v, sl) for k, v in x.items()}
+    if isinstance(x, (list, tuple)):
+        return [_take(v, sl) for v in x]
+    return _take(x, sl)
+
+
+def _take(v, sl):
+    if hasattr(v, "iloc"):
+        return v.iloc[sl]
+    return v[sl]
+
+
+class Feeder(object):
+    """Packs the per-feature host arrays of one batch into at most three pinned staging buffers
+    (int32 ids, int64 ids, fp32 dense/weights) so a step costs <= 3 H2D copies, and exposes every
+    model input as a column window of those packs."""
+
+    def __init__(self, model):
+        self.model = model
+        self.names = list(model.input_names)
+        self.specs = {t.name: t for t in model.inputs}
+        self.host_hash = {}
+        for s in model.planner.slots:
+            if s.hash[1] is not None:
+                self.host_hash[s.input_name] = s.hash[1]
+        self._pinned = {}
+        self.h2d_bytes = 0
+
+    def _as_dict(self, x):
+        if isinstance(x, dict):
+            return x
+        if isinstance(x, (list, tuple)):
+            if len(x) != len(self.names):
+                raise ValueError("model expects %d inputs %s, got %d arrays" % (len(self.names), self.names, len(x)))
+            return dict(zip(self.names, x))
+        if len(self.names) == 1:
+            return {self.names[0]: x}
+        raise ValueError("model inputs must be a dict or a list ordered like get_feature_names()")
+
+    _RING = 3
+
+    def _stage(self, key, shape, dtype):
+        """Pinned staging buffer from a small ring: a slot is reused only after the H2D copy that last
+        read it has completed (the host may run several steps ahead of the GPU)."""
+        ring = self._pinned.setdefault(key, {"slot": 0, "bufs": [None] * self._RING,
+                                             "events": [None] * self._RING})
+        i = ring["slot"] = (ring["slot"] + 1) % self._RING
+        n = int(np.prod(shape))
+        if ring["events"][i] is not None:
+            ring["events"][i].synchronize()
+        buf = ring["bufs"][i]
+        if buf is None or buf.numel() < n:
+            buf = torch.empty(max(n, 1), dtype=dtype)
+            try:
+                buf = buf.pin_memory()
+            except Exception:
+                pass
+            ring["bufs"][i] = buf
+        self._last_stage = (ring, i)
+        return buf[:n].reshape(shape)
+
+    def _copied(self):
+        ring, i = self._last_stage
+        ev = ring["events"][i]
+        if ev is None:
+            ev = ring["events"][i] = torch.cuda.Event()
+        ev.record()
+
+    def feed(self, x, batch_slice=None):
+        dev = E.device()
+        xd = self._as_dict(x)
+        groups = {"i32": [], "i64": [], "f32": []}
+        arrays = {}
+        for name in self.names:
+            if name not in xd:
+                raise ValueError("missing model input %r" % name)
+            spec = self.specs[name]
+            a = xd[name]
+            if isinstance(a, torch.Tensor) and a.is_cuda:
+                arrays[name] = ("dev", a)
+                continue
+            a = np.asarray(a.values if hasattr(a, "values") else a)
+            width = int(np.prod(spec.shape[1:])) if len(spec.shape) > 1 else 1
+            if name in self.host_hash:
+                a = host_hash(a, self.host_hash[name])
+            if a.dtype.kind in ("U", "S", "O"):
+                raise ValueError("input %r holds strings: declare the SparseFeat with use_hash=True" % name)
+            a = a.reshape(a.shape[0], -1) if a.ndim != 2 or a.shape[1] != width else a
+            if a.shape[1] != width:
+                raise ValueError("input %r: expected %d values per sample, got %s" % (name, width, a.shape))
+            if spec.dtype in ("float32", "float64", "float16"):
+                groups["f32"].append((name, a, width))
+            elif a.dtype == np.int64 and (spec.dtype == "int64" or a.size and
+                                          (a.max(initial=0) > 2 ** 31 - 1 or a.min(initial=0) < -2 ** 31)):
+                groups["i64"].append((name, a, width))
+            else:
+                groups["i32"].append((name, a, width))
+        feed = {}
+        np_dt = {"i32": np.int32, "i64": np.int64, "f32": np.float32}
+        th_dt = {"i32": torch.int32, "i64": torch.int64, "f32": torch.float32}
+        for key, items in groups.items():
+            if not items:
+                continue
+            b = items[0][1].shape[0]
+            total = sum(w for _, _, w in items)
+            stage = self._stage(key, (b, total), th_dt[key])
+            sn = stage.numpy()
+            col = 0
+            for name, a, w in items:
+                sn[:, col:col + w] = a
+                col += w
+            pack = stage.to(dev, non_blocking=True)
+            self._copied()
+            self.h2d_bytes += stage.numel() * stage.element_size()
+            base = E.Var(pack, name="__dense_pack__" if key == "f32" else "__id_pack_%s__" % key)
+            if key == "f32":
+                feed["__dense_pack__"] = base
+            col = 0
+            for name, a, w in items:
+                spec = self.specs[name]
+                shape = (b,) + tuple(int(s) for s in spec.shape[1:])
+                view = pack[:, col:col + w]
+                if key == "f32":
+                    v = E.Var(view.as_strided(shape, (pack.stride(0),) + _dense_strides(shape[1:]),
+                                              pack.storage_offset() + col),
+                              base=base, col0=col, ncols=w)
+                else:
+                    v = E.Var(view)
+                v.name = name
+                feed[name] = v
+                col += w
+        # device-resident inputs: float columns that are views of one [B, nd] buffer form a dense pack
+        packs = {}
+        for name, (_, a) in arrays.items():
+            if (a.dtype == torch.float32 and a.dim() == 2 and a.stride(1) == 1 and a.shape[0] > 1
+                    and "__dense_pack__" not in feed):
+                packs.setdefault((a.untyped_storage().data_ptr(), a.stride(0)), []).append((name, a))
+        done = set()
+        for (_, ld), items in packs.items():
+            lo = min(a.storage_offset() for _, a in items)
+            if len(items) < 2 or any(a.storage_offset() - lo + a.shape[1] > ld for _, a in items):
+                continue
+            first = items[0][1]
+            base_t = first.as_strided((first.shape[0], ld), (ld, 1), lo)
+            base = E.Var(base_t, name="__dense_pack__")
+            feed["__dense_pack__"] = base
+            for name, a in items:
+                v = E.Var(a, base=base, col0=a.storage_offset() - lo, ncols=a.shape[1])
+                v.name = name
+                feed[name] = v
+                done.add(name)
+            break
+        for name, (_, a) in arrays.items():
+            if name not in done:
+                feed[name] = E.Var(a)
+        return feed
+
+    def labels(self, y):
+        if isinstance(y, torch.Tensor) and y.is_cuda:
+            return y.reshape(-1).float()
+        a = np.asarray(y, dtype=np.float32).reshape(-1)
+        stage = self._stage("labels", (a.shape[0],), torch.float32)
+        stage.numpy()[:] = a
+        self.h2d_bytes += a.nbytes
+        out = stage.to(E.device(), non_blocking=True)
+        self._copied()
+        return out
+
+
+def _dense_strides(shape):
+    out, acc = [], 1
+    for s in reversed(shape):
+        out.append(acc)
+        acc *= s
+    return tuple(reversed(out))
+
+
+def host_hash(a, hash_layer):
+    """Host-side Hash for string ids / vocabulary files (deepctr/layers/utils.py:89-112): strings never
+    reach the device; integers are hashed on the device by the gather kernel itself."""
+    from .layers.utils import host_hash_array
+    return host_hash_array(a, hash_layer.num_buckets, hash_layer.mask_zero, hash_layer.vocabulary_path,
+                           hash_layer.default_value)

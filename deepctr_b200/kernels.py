@@ -207,6 +207,26 @@ def fill(dst, value):
     return dst
 
 
+def mask_nonzero_and(ids, inout=None):
+    """uint8 mask [B,T] of ids != 0, AND-ed into ``inout`` when given."""
+    _require_cuda(ids, inout)
+    first = inout is None
+    if first:
+        inout = torch.empty(ids.shape, dtype=torch.uint8, device=ids.device)
+    L.check(L.lib().b2ctr_mask_nonzero_and(ptr(ids), idx_dtype(ids), ids.numel(), ptr(inout), int(first),
+                                           stream()), "mask_nonzero_and")
+    return inout
+
+
+def mask_from_len(lengths, maxlen):
+    _require_cuda(lengths)
+    lengths = lengths.reshape(-1)
+    out = torch.empty((lengths.shape[0], maxlen), dtype=torch.uint8, device=lengths.device)
+    L.check(L.lib().b2ctr_mask_from_len(ptr(lengths), lengths.shape[0], maxlen, ptr(out), stream()),
+            "mask_from_len")
+    return out
+
+
 def copy2d(src, ld_src, dst, ld_dst, rows, cols, accumulate=False, src_off=0, dst_off=0):
     _require_cuda(src, dst)
     sp = C.c_void_p(src.data_ptr() + 4 * src_off)
@@ -274,3 +294,42 @@ def adagrad_step(w, g, acc, lr, eps=1e-7, l2=0.0):
     _require_cuda(w, g, acc)
     L.check(L.lib().b2ctr_adagrad_step(ptr(w), ptr(g), ptr(acc), lr, eps, l2, w.numel(), stream()),
             "adagrad_step")
+
+
+# ---- optional per-kernel timing (bench.py): CUDA events around each launch on the launching stream --
+PROFILE = None
+
+
+def _timed(fn):
+    name = fn.__name__
+
+    def wrap(*a, **k):
+        prof = PROFILE
+        if prof is None:
+            return fn(*a, **k)
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        r = fn(*a, **k)
+        e1.record()
+        prof.setdefault(name, []).append((e0, e1))
+        return r
+
+    wrap.__name__ = name
+    wrap.__doc__ = fn.__doc__
+    return wrap
+
+
+def profile_summary():
+    """{kernel wrapper name: (launch groups, total ms)} for everything recorded into PROFILE."""
+    torch.cuda.synchronize()
+    out = {}
+    for name, evs in (PROFILE or {}).items():
+        out[name] = (len(evs), float(sum(a.elapsed_time(b) for a, b in evs)))
+    return out
+
+
+for _n in ("embed_gather_fwd", "embed_scatter_add", "embed_gather_uniform_fwd", "embed_scatter_uniform_bwd",
+           "hash64", "gemm", "bias_act_bwd", "act_fwd", "add_n", "axpy", "fill", "copy2d", "rowsum", "fm_fwd",
+           "fm_bwd", "predict_loss", "sgd_step", "adam_step", "adagrad_step", "mask_nonzero_and",
+           "mask_from_len"):
+    globals()[_n] = _timed(globals()[_n])

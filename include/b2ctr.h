@@ -122,6 +122,8 @@ typedef struct b2ctr_uniform_gather {
   float* fm;                    /* [B] or NULL                                                  */
   int64_t ldx;
   int64_t dense_ld;
+  int64_t x_cols;               /* columns of x this call owns: [F*dim+ndense, x_cols) is zero-filled;
+                                   0 means ldx (other features may live in x beyond x_cols)        */
   int32_t nfeat;
   int32_t ndense;
   uint64_t fm_mask[2];
@@ -204,6 +206,13 @@ B2CTR_API b2ctr_status_t b2ctr_copy2d(const float* src, int64_t ld_src, float* d
 B2CTR_API b2ctr_status_t b2ctr_rowsum(const float* x, int64_t ld, float* out, int64_t rows,
                                      int64_t cols, void* stream);
 B2CTR_API b2ctr_status_t b2ctr_fill(float* dst, float value, int64_t n, void* stream);
+/* Keras masks as uint8 [B,T]: inout[i] = (first ? 1 : inout[i]) & (ids[i] != 0)   (Embedding mask_zero,
+ * AND-ed across concatenated features, deepctr/layers/utils.py:198-228) */
+B2CTR_API b2ctr_status_t b2ctr_mask_nonzero_and(const void* ids, int32_t idx_dtype, int64_t n,
+                                               uint8_t* inout, int32_t first, void* stream);
+/* tf.sequence_mask: out[b,t] = t < len[b] */
+B2CTR_API b2ctr_status_t b2ctr_mask_from_len(const int32_t* len, int64_t batch, int32_t maxlen,
+                                            uint8_t* out, void* stream);
 
 /* FM second-order term on [B,F,E] (deepctr/layers/interaction.py:588-604) and its Jacobian */
 B2CTR_API b2ctr_status_t b2ctr_fm_fwd(const float* x, int64_t ldx, int32_t nfield, int32_t dim,

@@ -1,0 +1,102 @@
+"""GPU parity of the DeepFM path end to end (feature columns -> fused gather -> FM -> DNN -> logit ->
+loss -> backward -> update) against the CPU oracle.  Tolerance from BASELINE.json's north_star:
+fp32 logits within 1e-4 relative."""
+import numpy as np
+import pytest
+import torch
+
+from oracle import models as OM
+from oracle import ops as O
+from tests import helpers as H
+
+pytestmark = pytest.mark.gpu
+
+
+def _build(rng, **kw):
+    from deepctr_b200.models import DeepFM
+    cols, x, y = H.criteo_like(rng, kw.pop("n", 96), **kw)
+    model = DeepFM(cols, cols, dnn_hidden_units=(32, 16), l2_reg_linear=0, l2_reg_embedding=0)
+    H.randomize_weights(model, rng)
+    return model, cols, x, y
+
+
+@pytest.mark.parametrize("dim", [8, 6])     # 8: Criteo fast path; 6: generic gather + standalone FM
+def test_deepfm_forward_matches_oracle(cuda, dim):
+    rng = np.random.RandomState(11)
+    model, cols, x, y = _build(rng, dim=dim)
+    model.compile("sgd", "binary_crossentropy", embedding_update="dense")
+    W = H.oracle_weights(model)
+    logit, want = OM.deepfm(x, cols, cols, W)
+    for rep in range(3):      # step 0 unfused, later steps run the fused FM / linear / dense tail
+        got = model.predict(x, batch_size=64)
+        assert got.shape == (len(y), 1)
+        assert H.rel_err(got, want.numpy()) < 1e-4, "rep %d" % rep
+    if dim == 8:
+        p = model.planner
+        assert p.fast and p.fm_hint is not None and p.lin_hint and p.tail_hint is not None
+
+
+@pytest.mark.parametrize("mode", ["dense", "sparse"])
+def test_deepfm_train_step_matches_oracle_sgd(cuda, mode):
+    rng = np.random.RandomState(12)
+    model, cols, x, y = _build(rng)
+    from deepctr_b200.engine import SGD
+    lr = 0.05
+    model.compile(SGD(lr), "binary_crossentropy", embedding_update=mode)
+    for step in range(3):     # covers the unfused first step and the fused later ones
+        W = H.oracle_weights(model, requires_grad=True)
+        logit, pred = OM.deepfm(x, cols, cols, W)
+        loss = O.binary_crossentropy(y, pred)
+        loss.backward()
+        got_loss = model.train_on_batch(x, y)
+        assert abs(got_loss - loss.item()) < 1e-4 * max(1.0, abs(loss.item()))
+        W2 = H.oracle_weights(model)
+        new, old = H.flat_params(W2), H.flat_params(W)
+        for name, p in old.items():
+            if p.grad is None:
+                continue
+            want = (p.detach() - lr * p.grad).numpy()
+            got = new[name].numpy()
+            scale = np.abs(lr * p.grad.numpy()).max() + 1e-12
+            err = np.abs(got - want).max() / scale
+            assert err < 2e-3, "step %d weight %s: update mismatch %.3e (relative to max update)" % (step, name, err)
+
+
+def test_deepfm_adam_dense_matches_keras_semantics(cuda):
+    """Keras Adam is dense over the tables: every row moves once m, v are non-zero."""
+    rng = np.random.RandomState(13)
+    model, cols, x, y = _build(rng)
+    model.compile("adam", "binary_crossentropy", embedding_update="dense")
+    tabs_before = {w.name: w.value() for w in model.planner.tables()}
+    l0 = model.train_on_batch(x, y)
+    l1 = model.train_on_batch(x, y)
+    for _ in range(20):
+        l2 = model.train_on_batch(x, y)
+    assert l2 < l0
+    hist = model.fit(x, y, batch_size=32, epochs=2, verbose=0, validation_split=0.25)
+    assert len(hist.history["loss"]) == 2 and len(hist.history["val_loss"]) == 2
+    ev = model.evaluate(x, y, batch_size=50)
+    assert np.isfinite(ev)
+
+
+def test_inputs_as_list_and_2d_columns(cuda):
+    """Appendix F.1: inputs may be a list ordered like get_feature_names, columns [N] or [N,1]."""
+    from deepctr_b200.feature_column import get_feature_names
+    rng = np.random.RandomState(14)
+    model, cols, x, y = _build(rng)
+    names = get_feature_names(cols)
+    a = model.predict(x, batch_size=256)
+    b = model.predict([x[n].reshape(-1, 1) for n in names], batch_size=17)
+    np.testing.assert_allclose(a, b, rtol=1e-6, atol=1e-7)
+
+
+def test_save_and_load_weights_roundtrip(cuda, tmp_path):
+    rng = np.random.RandomState(15)
+    model, cols, x, y = _build(rng)
+    a = model.predict(x, batch_size=256)
+    p = str(tmp_path / "w")
+    model.save_weights(p)
+    for w in model.weights:
+        w.set_value(np.zeros(w.shape, np.float32))
+    model.load_weights(p)
+    np.testing.assert_array_equal(a, model.predict(x, batch_size=256))

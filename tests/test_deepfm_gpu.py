@@ -7,7 +7,7 @@ import torch
 
 from oracle import models as OM
 from oracle import ops as O
-from tests import helpers as H
+import b2_helpers as H
 
 pytestmark = pytest.mark.gpu
 

@@ -37,7 +37,7 @@ class Feature(C.Structure):
                 ("out_col", C.c_int32), ("dim", C.c_int32), ("maxlen", C.c_int32),
                 ("idx_dtype", C.c_int32), ("pool", C.c_int32), ("mask_mode", C.c_int32),
                 ("hash_mode", C.c_int32), ("weight_mode", C.c_int32), ("src_table", C.c_void_p),
-                ("reserved", C.c_int32 * 2)]
+                ("len_stride", C.c_int32), ("weight_ld", C.c_int32)]
 
 
 class UniformGather(C.Structure):
@@ -92,6 +92,35 @@ SIGNATURES = {
     "b2ctr_sgd_step": (_i32, [_vp, _vp, _f32, _f32, _i64, _vp]),
     "b2ctr_adam_step": (_i32, [_vp, _vp, _vp, _vp, _f32, _f32, _f32, _f32, _f32, _i64, _i64, _vp]),
     "b2ctr_adagrad_step": (_i32, [_vp, _vp, _vp, _f32, _f32, _f32, _i64, _vp]),
+    "b2ctr_ewise": (_i32, [_i32, _vp, _vp, _vp, _vp, _i64, _i32, _vp]),
+    "b2ctr_cross_vector_fwd": (_i32, [_vp, _i64, _vp, _i64, _vp, _vp, _vp, _vp, _i64, _i32, _vp]),
+    "b2ctr_cross_vector_bwd": (_i32, [_vp, _i64, _vp, _vp, _vp, _vp, _vp, _vp, _i64, _i32, _vp]),
+    "b2ctr_cin_outer_fwd": (_i32, [_vp, _i64, _i64, _i64, _vp, _i64, _i64, _i64, _vp, _i64, _i32, _i32, _i32,
+                                   _vp]),
+    "b2ctr_cin_outer_bwd": (_i32, [_vp, _vp, _i64, _i64, _i64, _vp, _i64, _i64, _i64, _vp, _i64, _i64, _i64,
+                                   _i32, _vp, _i64, _i64, _i64, _i32, _i64, _i32, _i32, _i32, _vp]),
+    "b2ctr_cin_sum_d": (_i32, [_vp, _i64, _i32, _i32, _i32, _vp, _i64, _i32, _i64, _vp]),
+    "b2ctr_cin_expand_grad": (_i32, [_vp, _i64, _i32, _i32, _i32, _vp, _i64, _i32, _vp, _i64, _i32, _i64, _vp]),
+    "b2ctr_interacting_fwd": (_i32, [_vp, _vp, _vp, _vp, _vp, _i64, _i32, _i32, _i32, _i32, _vp]),
+    "b2ctr_interacting_bwd": (_i32, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i64, _i32, _i32, _i32,
+                                     _i32, _vp]),
+    "b2ctr_din_att_input_fwd": (_i32, [_vp, _i64, _vp, _i64, _vp, _i64, _i32, _i32, _vp]),
+    "b2ctr_din_att_input_bwd": (_i32, [_vp, _i64, _vp, _i64, _vp, _vp, _vp, _i64, _i32, _i32, _vp]),
+    "b2ctr_din_pool_fwd": (_i32, [_vp, _vp, _i64, _vp, _vp, _vp, _i64, _i32, _i32, _i32, _i32, _vp]),
+    "b2ctr_din_pool_bwd": (_i32, [_vp, _vp, _i64, _vp, _vp, _vp, _vp, _i64, _i32, _i32, _i32, _i32, _vp]),
+    "b2ctr_seqpool_fwd": (_i32, [_vp, _vp, _vp, _vp, _i64, _i32, _i32, _i32, _vp]),
+    "b2ctr_seqpool_bwd": (_i32, [_vp, _vp, _vp, _vp, _vp, _i64, _i32, _i32, _i32, _vp]),
+    "b2ctr_seqweight": (_i32, [_vp, _vp, _vp, _vp, _i64, _i32, _i32, _vp]),
+    "b2ctr_seqscale": (_i32, [_vp, _vp, _vp, _i64, _i32, _vp]),
+    "b2ctr_colstats_workspace_bytes": (_sz, [_i64, _i64]),
+    "b2ctr_colstats": (_i32, [_vp, _i64, _i64, _i64, _vp, _vp, _sz, _vp]),
+    "b2ctr_moving_update": (_i32, [_vp, _vp, _f32, _i64, _vp]),
+    "b2ctr_bn_apply": (_i32, [_vp, _vp, _vp, _vp, _vp, _vp, _i64, _i64, _f32, _vp]),
+    "b2ctr_bn_bwd": (_i32, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i64, _i64, _f32, _i32, _vp, _sz, _vp]),
+    "b2ctr_dice_fwd": (_i32, [_vp, _vp, _vp, _vp, _vp, _i64, _i64, _f32, _vp]),
+    "b2ctr_dice_bwd_workspace_bytes": (_sz, [_i64, _i64]),
+    "b2ctr_dice_bwd": (_i32, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _i64, _i64, _f32, _i32, _vp, _sz, _vp]),
+    "b2ctr_dropout": (_i32, [_vp, _vp, _i64, _f32, _u64, _vp]),
 }
 
 

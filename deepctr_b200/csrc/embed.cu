@@ -162,6 +162,10 @@ __device__ __forceinline__ float4 vmax(float4 a, float4 b) {
 }
 __device__ __forceinline__ float vmax(float a, float b) { return fmaxf(a, b); }
 
+// strides of the optional per-sample side inputs (0 = dense default)
+__device__ __forceinline__ int64_t wld(const b2ctr_feature_t& ft) { return ft.weight_ld > 0 ? ft.weight_ld : ft.maxlen; }
+__device__ __forceinline__ int64_t lstride(const b2ctr_feature_t& ft) { return ft.len_stride > 0 ? ft.len_stride : 1; }
+
 struct SeqInfo {
   float L;      // float(valid length) as the reference computes it
   float wmax;   // softmax max
@@ -179,7 +183,7 @@ __device__ __forceinline__ bool pos_valid(const b2ctr_feature_t& ft, int t, int6
 __device__ __forceinline__ float pos_weight(const b2ctr_feature_t& ft, const SeqInfo& si, int64_t b,
                                             int t, bool valid) {
   if (ft.weight_mode == B2CTR_WEIGHT_NONE) return 1.f;
-  float w = ft.weight[b * ft.maxlen + t];
+  float w = ft.weight[b * wld(ft) + t];
   if (ft.weight_mode == B2CTR_WEIGHT_RAW) return valid ? w : 0.f;
   float wt = valid ? w : -4294967295.f;  // -2^32+1 rounds to -2^32 in fp32, as in TF
   return __fdiv_rn(expf(__fsub_rn(wt, si.wmax)), si.wsum);
@@ -191,7 +195,7 @@ __device__ SeqInfo seq_info(const b2ctr_feature_t& ft, int64_t b) {
   si.wmax = 0.f;
   si.wsum = 1.f;
   const int T = ft.maxlen;
-  const int len = ft.mask_mode == B2CTR_MASK_LENGTH ? ft.len[b] : 0;
+  const int len = ft.mask_mode == B2CTR_MASK_LENGTH ? ft.len[b * lstride(ft)] : 0;
   if (ft.mask_mode == B2CTR_MASK_LENGTH) {
     si.L = (float)len;
   } else if (ft.mask_mode == B2CTR_MASK_ZERO_ID) {
@@ -206,14 +210,14 @@ __device__ SeqInfo seq_info(const b2ctr_feature_t& ft, int64_t b) {
     for (int t = 0; t < T; ++t) {
       int64_t id = ft.mask_mode == B2CTR_MASK_ZERO_ID ? lookup_id(ft, b * ft.idx_stride + t) : 1;
       bool v = pos_valid(ft, t, id, len);
-      float w = v ? ft.weight[b * T + t] : -4294967295.f;
+      float w = v ? ft.weight[b * wld(ft) + t] : -4294967295.f;
       m = fmaxf(m, w);
     }
     float s = 0.f;
     for (int t = 0; t < T; ++t) {
       int64_t id = ft.mask_mode == B2CTR_MASK_ZERO_ID ? lookup_id(ft, b * ft.idx_stride + t) : 1;
       bool v = pos_valid(ft, t, id, len);
-      float w = v ? ft.weight[b * T + t] : -4294967295.f;
+      float w = v ? ft.weight[b * wld(ft) + t] : -4294967295.f;
       s = __fadd_rn(s, expf(__fsub_rn(w, m)));
     }
     si.wmax = m;
@@ -248,7 +252,7 @@ __global__ void __launch_bounds__(256)
       continue;
     }
 
-    const int len = ft.mask_mode == B2CTR_MASK_LENGTH ? ft.len[b] : 0;
+    const int len = ft.mask_mode == B2CTR_MASK_LENGTH ? ft.len[b * lstride(ft)] : 0;
     const SeqInfo si = seq_info(ft, b);
     for (int e = lane * VEC; e < dim; e += G * VEC) {
       V acc = vzero<VEC>();
@@ -314,7 +318,7 @@ __global__ void __launch_bounds__(256)
       }
       continue;
     }
-    const int len = ft.mask_mode == B2CTR_MASK_LENGTH ? ft.len[b] : 0;
+    const int len = ft.mask_mode == B2CTR_MASK_LENGTH ? ft.len[b * lstride(ft)] : 0;
     const SeqInfo si = seq_info(ft, b);
     for (int e = lane * VEC; e < dim; e += G * VEC) {
       V g = vmuls(vload(gout + e, (V*)nullptr), scale);

@@ -39,11 +39,13 @@ def device():
 class Var(object):
     """Runtime tensor.  ``data`` has the logical shape; when ``base`` is set, ``data`` is a strided
     window [col0, col0+ncols) of ``base.data`` (a [B, ld] buffer) and gradients are routed there."""
-    __slots__ = ("data", "grad", "requires_grad", "mask", "base", "col0", "ncols", "owner", "name")
+    __slots__ = ("data", "grad", "requires_grad", "mask", "base", "col0", "ncols", "owner", "name",
+                 "vshape")
 
     def __init__(self, data, requires_grad=False, mask=None, base=None, col0=0, ncols=0, owner=None,
-                 name=None):
+                 name=None, vshape=None):
         self.data = data
+        self.vshape = vshape    # logical shape of a VIRTUAL var (data is None: fused away this step)
         self.grad = None
         self.requires_grad = requires_grad
         self.mask = mask
@@ -55,10 +57,11 @@ class Var(object):
 
     @property
     def shape(self):
-        return tuple(self.data.shape)
+        return tuple(self.data.shape) if self.data is not None else tuple(self.vshape)
 
     def alias(self):
-        v = Var(self.data, self.requires_grad, self.mask, self.base, self.col0, self.ncols, self.owner)
+        v = Var(self.data, self.requires_grad, self.mask, self.base, self.col0, self.ncols, self.owner,
+                vshape=self.vshape)
         if self.base is None:
             v.base, v.col0, v.ncols = self, 0, -1   # whole-tensor alias: grads flow to the original
         return v
@@ -187,11 +190,19 @@ class KMask(object):
             return self._u8
         out = None
         if self.lengths is not None:
-            out = K.mask_from_len(self.lengths, self.maxlen)
+            ln = self.lengths
+            if not ln.is_contiguous():
+                from . import ops
+                ln = ops.dense_i32(ln.reshape(ln.shape[0], -1)).reshape(-1)
+            out = K.mask_from_len(ln, self.maxlen)
         for ids, hashed in self.terms:
             t = ids.reshape(ids.shape[0], -1)
             if not t.is_contiguous():
-                t = t.contiguous()
+                if t.dtype == torch.int32:
+                    from . import ops
+                    t = ops.dense_i32(t)
+                else:
+                    t = t.contiguous()
             if hashed is not None and hashed[0] == L.HASH_FARM:
                 raise L.B2ctrError("mask of a hashed feature without mask_zero is not defined by the reference")
             out = K.mask_nonzero_and(t, out)

@@ -492,7 +492,7 @@ class EmbeddingPlanner(object):
             if s.buf == "lin" and lin_fused:
                 base = E.Var(None, owner=self)       # virtual: only its row-sum exists this step
                 base.name = "__virtual_lin__"
-                out = E.Var(None, base=base, col0=s.col, ncols=s.dim, owner=self)
+                out = E.Var(None, base=base, col0=s.col, ncols=s.dim, owner=self, vshape=(batch, 1, s.dim))
             elif s.buf == "seq":
                 base = bufs[id(s)]
                 out = ops._window(base, 0, s.maxlen * s.dim, (batch, s.maxlen, s.dim))

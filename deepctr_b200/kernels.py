@@ -58,6 +58,9 @@ def make_feature(table, idx, out, out_col=0, out_ld=None, maxlen=1, pool=L.POOL_
     f.idx = idx.data_ptr()
     f.len = length.data_ptr() if length is not None else None
     f.weight = weight.data_ptr() if weight is not None else None
+    # side inputs may be column windows of a packed staging buffer: pass their sample strides
+    f.len_stride = length.stride(0) if (length is not None and length.dim() >= 1 and length.shape[0] > 1) else 0
+    f.weight_ld = weight.stride(0) if (weight is not None and weight.dim() >= 2 and weight.shape[0] > 1) else 0
     f.out = out.data_ptr()
     f.vocab = table.shape[0]
     f.dim = table.shape[1] if table.dim() > 1 else 1
@@ -332,4 +335,186 @@ for _n in ("embed_gather_fwd", "embed_scatter_add", "embed_gather_uniform_fwd", 
            "hash64", "gemm", "bias_act_bwd", "act_fwd", "add_n", "axpy", "fill", "copy2d", "rowsum", "fm_fwd",
            "fm_bwd", "predict_loss", "sgd_step", "adam_step", "adagrad_step", "mask_nonzero_and",
            "mask_from_len"):
+    globals()[_n] = _timed(globals()[_n])
+
+
+# ---- interaction / sequence operators ---------------------------------------------------------------
+def _lib_call(name, *args):
+    L.check(getattr(L.lib(), "b2ctr_" + name)(*args), name)
+
+
+def ewise(op, a, b, c=None, out=None, accumulate=False):
+    _require_cuda(a, b, c, out)
+    out = torch.empty_like(a) if out is None else out
+    _lib_call("ewise", op, ptr(a), ptr(b), ptr(c), ptr(out), a.numel(), int(accumulate), stream())
+    return out
+
+
+def cross_vector_fwd(x0, ld0, xl, ldl, w, bias, batch, dim):
+    out = torch.empty((batch, dim), dtype=torch.float32, device=x0.device)
+    s = torch.empty((batch,), dtype=torch.float32, device=x0.device)
+    _lib_call("cross_vector_fwd", ptr(x0), ld0, ptr(xl), ldl, ptr(w), ptr(bias), ptr(out), ptr(s), batch, dim,
+              stream())
+    return out, s
+
+
+def cross_vector_bwd(x0, ld0, w, dout, s, batch, dim):
+    dx0 = torch.empty((batch, dim), dtype=torch.float32, device=x0.device)
+    dxl = torch.empty((batch, dim), dtype=torch.float32, device=x0.device)
+    ds = torch.empty((batch,), dtype=torch.float32, device=x0.device)
+    _lib_call("cross_vector_bwd", ptr(x0), ld0, ptr(w), ptr(dout), ptr(s), ptr(dx0), ptr(dxl), ptr(ds), batch,
+              dim, stream())
+    return dx0, dxl, ds
+
+
+def _off(t, elems):
+    return C.c_void_p(t.data_ptr() + 4 * elems)
+
+
+def cin_outer_fwd(x0, v0, xk, vk, z, b0, nb, m, h, d):
+    """v0 / vk = (sb, si, sd) element strides; b0 = first sample of the chunk."""
+    _lib_call("cin_outer_fwd", _off(x0, b0 * v0[0]), v0[0], v0[1], v0[2], _off(xk, b0 * vk[0]), vk[0], vk[1],
+              vk[2], ptr(z), nb, m, h, d, stream())
+
+
+def cin_outer_bwd(dz, x0, v0, xk, vk, dx0, g0, acc0, dxk, gk, acck, b0, nb, m, h, d):
+    _lib_call("cin_outer_bwd", ptr(dz), _off(x0, b0 * v0[0]), v0[0], v0[1], v0[2], _off(xk, b0 * vk[0]), vk[0],
+              vk[1], vk[2], _off(dx0, b0 * g0[0]) if dx0 is not None else C.c_void_p(0), g0[0], g0[1], g0[2],
+              int(acc0), _off(dxk, b0 * gk[0]) if dxk is not None else C.c_void_p(0), gk[0], gk[1], gk[2],
+              int(acck), nb, m, h, d, stream())
+
+
+def cin_sum_d(y, ldy, col0, ncols, d, out, ldo, out_col, b0, nb):
+    _lib_call("cin_sum_d", ptr(y), ldy, col0, ncols, d, _off(out, b0 * ldo), ldo, out_col, nb, stream())
+
+
+def cin_expand_grad(dout, ldo, out_col, col0, ncols, dh, ldh, hcols, dy, nfilt, d, b0, nb):
+    _lib_call("cin_expand_grad", _off(dout, b0 * ldo), ldo, out_col, col0, ncols, ptr(dh), ldh, hcols, ptr(dy),
+              nfilt, d, nb, stream())
+
+
+def interacting_fwd(q, k, v, res, batch, F, H, D, scaling):
+    out = torch.empty_like(q)
+    _lib_call("interacting_fwd", ptr(q), ptr(k), ptr(v), ptr(res), ptr(out), batch, F, H, D, int(scaling),
+              stream())
+    return out
+
+
+def interacting_bwd(q, k, v, out, dout, want_res, batch, F, H, D, scaling):
+    dq, dk, dv = torch.empty_like(q), torch.empty_like(q), torch.empty_like(q)
+    dres = torch.empty_like(q) if want_res else None
+    _lib_call("interacting_bwd", ptr(q), ptr(k), ptr(v), ptr(out), ptr(dout), ptr(dq), ptr(dk), ptr(dv),
+              ptr(dres), batch, F, H, D, int(scaling), stream())
+    return dq, dk, dv, dres
+
+
+def din_att_input_fwd(q, ldq, keys, ldk, batch, T, E):
+    out = torch.empty((batch, T, 4 * E), dtype=torch.float32, device=q.device)
+    _lib_call("din_att_input_fwd", ptr(q), ldq, ptr(keys), ldk, ptr(out), batch, T, E, stream())
+    return out
+
+
+def din_att_input_bwd(q, ldq, keys, ldk, g, batch, T, E):
+    dq = torch.empty((batch, 1, E), dtype=torch.float32, device=q.device)
+    dk = torch.empty((batch, T, E), dtype=torch.float32, device=q.device)
+    _lib_call("din_att_input_bwd", ptr(q), ldq, ptr(keys), ldk, ptr(g), ptr(dq), ptr(dk), batch, T, E, stream())
+    return dq, dk
+
+
+def din_pool_fwd(score, keys, ldk, mask, batch, T, E, weight_norm, return_score):
+    w = torch.empty((batch, T), dtype=torch.float32, device=score.device)
+    out = torch.empty((batch, 1, T if return_score else E), dtype=torch.float32, device=score.device)
+    _lib_call("din_pool_fwd", ptr(score), ptr(keys), ldk, ptr(mask), ptr(w), ptr(out), batch, T, E,
+              int(weight_norm), int(return_score), stream())
+    return out, w
+
+
+def din_pool_bwd(w, keys, ldk, mask, dout, batch, T, E, weight_norm, return_score, want_dkeys=True):
+    dscore = torch.empty((batch, T, 1), dtype=torch.float32, device=w.device)
+    dkeys = torch.empty((batch, T, E), dtype=torch.float32, device=w.device) if (want_dkeys and not return_score) \
+        else None
+    _lib_call("din_pool_bwd", ptr(w), ptr(keys), ldk, ptr(mask), ptr(dout), ptr(dscore), ptr(dkeys), batch, T, E,
+              int(weight_norm), int(return_score), stream())
+    return dscore, dkeys
+
+
+def seqpool_fwd(x, mask, length, batch, T, E, mode):
+    out = torch.empty((batch, 1, E), dtype=torch.float32, device=x.device)
+    _lib_call("seqpool_fwd", ptr(x), ptr(mask), ptr(length), ptr(out), batch, T, E, mode, stream())
+    return out
+
+
+def seqpool_bwd(x, mask, length, dout, batch, T, E, mode):
+    dx = torch.empty((batch, T, E), dtype=torch.float32, device=x.device)
+    _lib_call("seqpool_bwd", ptr(x), ptr(mask), ptr(length), ptr(dout), ptr(dx), batch, T, E, mode, stream())
+    return dx
+
+
+def seqweight(w, mask, length, batch, T, normalize):
+    wt = torch.empty((batch, T), dtype=torch.float32, device=w.device)
+    _lib_call("seqweight", ptr(w), ptr(mask), ptr(length), ptr(wt), batch, T, int(normalize), stream())
+    return wt
+
+
+def seqscale(x, wt, rows, E):
+    out = torch.empty_like(x)
+    _lib_call("seqscale", ptr(x), ptr(wt), ptr(out), rows, E, stream())
+    return out
+
+
+def colstats(x, ld, m, n):
+    stats = torch.empty((2, n), dtype=torch.float32, device=x.device)
+    nbytes = L.lib().b2ctr_colstats_workspace_bytes(m, n)
+    ws = workspace(nbytes, x.device)
+    _lib_call("colstats", ptr(x), ld, m, n, ptr(stats), ptr(ws), nbytes, stream())
+    return stats
+
+
+def moving_update(moving, batch_stat, momentum):
+    _lib_call("moving_update", ptr(moving), ptr(batch_stat), momentum, moving.numel(), stream())
+
+
+def bn_apply(x, mean, var, gamma, beta, m, n, eps):
+    y = torch.empty_like(x)
+    _lib_call("bn_apply", ptr(x), ptr(mean), ptr(var), ptr(gamma), ptr(beta), ptr(y), m, n, eps, stream())
+    return y
+
+
+def bn_bwd(x, mean, var, gamma, dy, m, n, eps, training):
+    dx = torch.empty_like(x)
+    dgamma = torch.empty((n,), dtype=torch.float32, device=x.device)
+    dbeta = torch.empty((n,), dtype=torch.float32, device=x.device)
+    nbytes = L.lib().b2ctr_colstats_workspace_bytes(m, n)
+    ws = workspace(nbytes, x.device)
+    _lib_call("bn_bwd", ptr(x), ptr(mean), ptr(var), ptr(gamma), ptr(dy), ptr(dx), ptr(dgamma), ptr(dbeta), m, n,
+              eps, int(training), ptr(ws), nbytes, stream())
+    return dx, dgamma, dbeta
+
+
+def dice_fwd(x, mean, var, alpha, m, n, eps):
+    y = torch.empty_like(x)
+    _lib_call("dice_fwd", ptr(x), ptr(mean), ptr(var), ptr(alpha), ptr(y), m, n, eps, stream())
+    return y
+
+
+def dice_bwd(x, mean, var, alpha, dy, m, n, eps, training):
+    dx = torch.empty_like(x)
+    dalpha = torch.empty((n,), dtype=torch.float32, device=x.device)
+    nbytes = L.lib().b2ctr_dice_bwd_workspace_bytes(m, n)
+    ws = workspace(nbytes, x.device)
+    _lib_call("dice_bwd", ptr(x), ptr(mean), ptr(var), ptr(alpha), ptr(dy), ptr(dx), ptr(dalpha), m, n, eps,
+              int(training), ptr(ws), nbytes, stream())
+    return dx, dalpha
+
+
+def dropout(x, rate, seed):
+    y = torch.empty_like(x)
+    _lib_call("dropout", ptr(x), ptr(y), x.numel(), rate, seed & 0xFFFFFFFFFFFFFFFF, stream())
+    return y
+
+
+for _n in ("ewise", "cross_vector_fwd", "cross_vector_bwd", "cin_outer_fwd", "cin_outer_bwd", "cin_sum_d",
+           "cin_expand_grad", "interacting_fwd", "interacting_bwd", "din_att_input_fwd", "din_att_input_bwd",
+           "din_pool_fwd", "din_pool_bwd", "seqpool_fwd", "seqpool_bwd", "seqweight", "seqscale", "colstats",
+           "bn_apply", "bn_bwd", "dice_fwd", "dice_bwd", "dropout"):
     globals()[_n] = _timed(globals()[_n])

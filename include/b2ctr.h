@@ -88,7 +88,8 @@ typedef struct b2ctr_feature {
   int32_t weight_mode;   /* B2CTR_WEIGHT_*                                                       */
   const float* src_table;/* scatter only: table holding the FORWARD rows when `table` is a separate
                             gradient buffer (needed by max pooling to re-find the arg-max); NULL = table */
-  int32_t reserved[2];
+  int32_t len_stride;   /* elements between consecutive samples in len (0 = 1)                   */
+  int32_t weight_ld;    /* elements between consecutive samples in weight (0 = maxlen)            */
 } b2ctr_feature_t;
 
 #define B2CTR_MAX_FEATURES 128
@@ -243,6 +244,122 @@ B2CTR_API b2ctr_status_t b2ctr_adam_step(float* w, const float* g, float* m, flo
                                         int64_t step, int64_t n, void* stream);
 B2CTR_API b2ctr_status_t b2ctr_adagrad_step(float* w, const float* g, float* acc, float lr,
                                            float eps, float l2, int64_t n, void* stream);
+
+/* ------------------------------------------------------------------------------------------ */
+/* 5. Interaction operators                                                                     */
+/* ------------------------------------------------------------------------------------------ */
+/* out = a*b (op 0) or a*b + c (op 1), elementwise over n; accumulate: out += */
+B2CTR_API b2ctr_status_t b2ctr_ewise(int32_t op, const float* a, const float* b, const float* c,
+                                    float* out, int64_t n, int32_t accumulate, void* stream);
+
+/* CrossNet 'vector' layer (deepctr/layers/interaction.py:413-416):
+ *   s[b] = <xl[b], w>;  out[b] = x0[b]*s[b] + bias + xl[b]          (one warp per sample, shuffles)
+ * backward: dx0 = dout*s, dxl = dout + w*ds, ds[b] = <dout[b], x0[b]>; dw = xl^T ds and
+ * dbias = colsum(dout) are left to b2ctr_gemm / b2ctr_bias_act_bwd.                            */
+B2CTR_API b2ctr_status_t b2ctr_cross_vector_fwd(const float* x0, int64_t ld0, const float* xl,
+                                               int64_t ldl, const float* w, const float* bias,
+                                               float* out, float* s, int64_t batch, int32_t dim,
+                                               void* stream);
+B2CTR_API b2ctr_status_t b2ctr_cross_vector_bwd(const float* x0, int64_t ld0, const float* w,
+                                               const float* dout, const float* s, float* dx0,
+                                               float* dxl, float* ds, int64_t batch, int32_t dim,
+                                               void* stream);
+
+/* CIN (deepctr/layers/interaction.py:277-325).  X(b,i,d) = x[b*sb + i*si + d*sd].
+ * outer_fwd: z[(b,d), i*h + j] = X0(b,i,d) * Xk(b,j,d) for a batch chunk sized to stay in L2; the
+ * contraction z @ filter runs through b2ctr_gemm.  outer_bwd folds d z back onto X0 / Xk.       */
+B2CTR_API b2ctr_status_t b2ctr_cin_outer_fwd(const float* x0, int64_t s0b, int64_t s0i, int64_t s0d,
+                                            const float* xk, int64_t skb, int64_t ski, int64_t skd,
+                                            float* z, int64_t nb, int32_t m, int32_t h, int32_t d,
+                                            void* stream);
+B2CTR_API b2ctr_status_t b2ctr_cin_outer_bwd(const float* dz, const float* x0, int64_t s0b, int64_t s0i,
+                                            int64_t s0d, const float* xk, int64_t skb, int64_t ski,
+                                            int64_t skd, float* dx0, int64_t g0b, int64_t g0i,
+                                            int64_t g0d, int32_t acc0, float* dxk, int64_t gkb,
+                                            int64_t gki, int64_t gkd, int32_t acck, int64_t nb,
+                                            int32_t m, int32_t h, int32_t d, void* stream);
+/* out[b, out_col+n] = sum_d y[(b,d), col0+n]  (reduce_sum over D of the direct maps, :322-323) */
+B2CTR_API b2ctr_status_t b2ctr_cin_sum_d(const float* y, int64_t ldy, int32_t col0, int32_t ncols,
+                                        int32_t d, float* out, int64_t ldo, int32_t out_col,
+                                        int64_t nb, void* stream);
+/* dy[(b,d), n] = [col0 <= n < col0+ncols] dout[b, out_col+n-col0] + [n < hcols] dh[(b,d), n] */
+B2CTR_API b2ctr_status_t b2ctr_cin_expand_grad(const float* dout, int64_t ldo, int32_t out_col,
+                                              int32_t col0, int32_t ncols, const float* dh,
+                                              int64_t ldh, int32_t hcols, float* dy, int64_t nfilt,
+                                              int32_t d, int64_t nb, void* stream);
+
+/* InteractingLayer attention core (deepctr/layers/interaction.py:760-777) on projected
+ * q/k/v[/res] of shape [B, F, heads*dhead]: out = relu(softmax(q_h k_h^T [/sqrt(d)]) v_h + res). */
+B2CTR_API b2ctr_status_t b2ctr_interacting_fwd(const float* q, const float* k, const float* v,
+                                              const float* res, float* out, int64_t batch,
+                                              int32_t nfield, int32_t heads, int32_t dhead,
+                                              int32_t scaling, void* stream);
+B2CTR_API b2ctr_status_t b2ctr_interacting_bwd(const float* q, const float* k, const float* v,
+                                              const float* out, const float* dout, float* dq,
+                                              float* dk, float* dv, float* dres, int64_t batch,
+                                              int32_t nfield, int32_t heads, int32_t dhead,
+                                              int32_t scaling, void* stream);
+
+/* ------------------------------------------------------------------------------------------ */
+/* 6. Sequence operators (DIN, pooling, Dice / BatchNormalization, dropout)                     */
+/* ------------------------------------------------------------------------------------------ */
+/* LocalActivationUnit input (deepctr/layers/core.py:98-101): out[b,t] = [q, k, q-k, q*k] */
+B2CTR_API b2ctr_status_t b2ctr_din_att_input_fwd(const float* q, int64_t ldq, const float* keys,
+                                                int64_t ldk, float* out, int64_t batch, int32_t T,
+                                                int32_t E, void* stream);
+B2CTR_API b2ctr_status_t b2ctr_din_att_input_bwd(const float* q, int64_t ldq, const float* keys,
+                                                int64_t ldk, const float* g, float* dq, float* dk,
+                                                int64_t batch, int32_t T, int32_t E, void* stream);
+/* AttentionSequencePoolingLayer tail (deepctr/layers/sequence.py:278-291): masked fill (0 or
+ * -2^32+1 + softmax), then out = w @ keys (or the weights themselves when return_score).      */
+B2CTR_API b2ctr_status_t b2ctr_din_pool_fwd(const float* score, const float* keys, int64_t ldk,
+                                           const uint8_t* mask, float* w, float* out, int64_t batch,
+                                           int32_t T, int32_t E, int32_t weight_norm,
+                                           int32_t return_score, void* stream);
+B2CTR_API b2ctr_status_t b2ctr_din_pool_bwd(const float* w, const float* keys, int64_t ldk,
+                                           const uint8_t* mask, const float* dout, float* dscore,
+                                           float* dkeys, int64_t batch, int32_t T, int32_t E,
+                                           int32_t weight_norm, int32_t return_score, void* stream);
+/* SequencePoolingLayer on a materialised [B,T,E] tensor (deepctr/layers/sequence.py:76-106);
+ * mode = B2CTR_POOL_SUM/MEAN/MAX; validity from mask (uint8 [B,T]) or len ([B]).               */
+B2CTR_API b2ctr_status_t b2ctr_seqpool_fwd(const float* x, const uint8_t* mask, const int32_t* len,
+                                          float* out, int64_t batch, int32_t T, int32_t E,
+                                          int32_t mode, void* stream);
+B2CTR_API b2ctr_status_t b2ctr_seqpool_bwd(const float* x, const uint8_t* mask, const int32_t* len,
+                                          const float* dout, float* dx, int64_t batch, int32_t T,
+                                          int32_t E, int32_t mode, void* stream);
+/* WeightedSequenceLayer (deepctr/layers/sequence.py:155-183): wt = masked [soft-maxed] weights;
+ * seqscale: out[r, :] = x[r, :] * wt[r]                                                        */
+B2CTR_API b2ctr_status_t b2ctr_seqweight(const float* w, const uint8_t* mask, const int32_t* len,
+                                        float* wt, int64_t batch, int32_t T, int32_t normalize,
+                                        void* stream);
+B2CTR_API b2ctr_status_t b2ctr_seqscale(const float* x, const float* wt, float* out, int64_t rows,
+                                       int32_t E, void* stream);
+/* column mean / biased variance of x[m,n] -> stats[0:n], stats[n:2n] (deterministic two-pass) */
+B2CTR_API size_t b2ctr_colstats_workspace_bytes(int64_t m, int64_t n);
+B2CTR_API b2ctr_status_t b2ctr_colstats(const float* x, int64_t ld, int64_t m, int64_t n, float* stats,
+                                       void* workspace, size_t workspace_bytes, void* stream);
+B2CTR_API b2ctr_status_t b2ctr_moving_update(float* moving, const float* batch, float momentum,
+                                            int64_t n, void* stream);
+B2CTR_API b2ctr_status_t b2ctr_bn_apply(const float* x, const float* mean, const float* var,
+                                       const float* gamma, const float* beta, float* y, int64_t m,
+                                       int64_t n, float eps, void* stream);
+B2CTR_API b2ctr_status_t b2ctr_bn_bwd(const float* x, const float* mean, const float* var,
+                                     const float* gamma, const float* dy, float* dx, float* dgamma,
+                                     float* dbeta, int64_t m, int64_t n, float eps, int32_t training,
+                                     void* workspace, size_t workspace_bytes, void* stream);
+/* Dice (deepctr/layers/activation.py:59-64): p = sigmoid(BN(x)); y = alpha*(1-p)*x + p*x */
+B2CTR_API b2ctr_status_t b2ctr_dice_fwd(const float* x, const float* mean, const float* var,
+                                       const float* alpha, float* y, int64_t m, int64_t n, float eps,
+                                       void* stream);
+B2CTR_API size_t b2ctr_dice_bwd_workspace_bytes(int64_t m, int64_t n);
+B2CTR_API b2ctr_status_t b2ctr_dice_bwd(const float* x, const float* mean, const float* var,
+                                       const float* alpha, const float* dy, float* dx, float* dalpha,
+                                       int64_t m, int64_t n, float eps, int32_t training,
+                                       void* workspace, size_t workspace_bytes, void* stream);
+/* y = keep(seed, i) ? x / (1 - rate) : 0   (the backward applies the same call to dy) */
+B2CTR_API b2ctr_status_t b2ctr_dropout(const float* x, float* y, int64_t n, float rate, uint64_t seed,
+                                      void* stream);
 
 #ifdef __cplusplus
 }

@@ -1,0 +1,308 @@
+"""GPU parity of every hot-path operator layer (forward + gradients) against the CPU oracle.
+Parametrisation follows the reference's own layer tests (tests/layers/interaction_test.py:11-126,
+sequence_test.py:17-51, core_test.py:15-65, activations_test.py) with real numeric assertions added."""
+import numpy as np
+import pytest
+import torch
+
+from oracle import ops as O
+import b2_helpers as H
+
+pytestmark = pytest.mark.gpu
+RTOL, ATOL = 1e-4, 1e-5
+
+
+def _run(layer, inputs, grad_out_rng, training=False):
+    """Eager forward + backward of a layer.  Returns (output numpy, [input grads], {weight name: grad})."""
+    from deepctr_b200 import engine as E
+    vars_in = E._map_structure(E.to_var, inputs)
+    for v in E._flatten(vars_in):
+        if v.data.dtype == torch.float32:
+            v.requires_grad = True
+    tape = E.Tape()
+    with E.recording(tape):
+        layer._maybe_build(E._shape_of(vars_in))
+        for w in layer.weights:
+            w.materialize()
+        y = layer._invoke(vars_in, training)
+    out = E.contiguous(y).cpu().numpy()
+    gy = grad_out_rng.normal(size=out.shape).astype(np.float32)
+    y.requires_grad = True
+    E.add_grad(y, torch.from_numpy(gy).to(y.data.device))
+    tape.backward()
+    gin = [v.grad.cpu().numpy().reshape(v.shape) if v.grad is not None else None for v in E._flatten(vars_in)]
+    gw = {w.name.split("/", 1)[1]: (w.grad.cpu().numpy() if w.grad is not None else None) for w in layer.weights}
+    return out, gy, gin, gw
+
+
+def _t(a, grad=True):
+    return torch.tensor(np.asarray(a), requires_grad=grad)
+
+
+def _close(a, b, rtol=RTOL, atol=ATOL):
+    np.testing.assert_allclose(np.asarray(a), np.asarray(b), rtol=rtol, atol=atol)
+
+
+def test_fm_layer(cuda):
+    from deepctr_b200.layers import FM
+    rng = np.random.RandomState(0)
+    x = rng.normal(size=(5, 4, 3)).astype(np.float32)
+    out, gy, gin, _ = _run(FM(), x, rng)
+    xt = _t(x)
+    want = O.fm(xt)
+    (want * _t(gy, False)).sum().backward()
+    _close(out, want.detach())
+    _close(gin[0], xt.grad)
+    with pytest.raises(ValueError):
+        FM()(np.zeros((3, 4), np.float32))
+
+
+@pytest.mark.parametrize("layer_num,param", [(0, "vector"), (1, "vector"), (3, "vector"), (2, "matrix")])
+def test_crossnet(cuda, layer_num, param):
+    from deepctr_b200.layers import CrossNet
+    rng = np.random.RandomState(1)
+    x = rng.normal(size=(33, 7)).astype(np.float32)
+    layer = CrossNet(layer_num, parameterization=param)
+    layer.build((None, 7))
+    for w in layer.weights:
+        w.set_value(rng.normal(0, 0.3, size=w.shape).astype(np.float32))
+    out, gy, gin, gw = _run(layer, x, rng)
+    xt = _t(x)
+    ks = [_t(w.value()) for w in layer.kernels]
+    bs = [_t(w.value()) for w in layer.bias]
+    want = O.crossnet(xt, ks, bs, param)
+    (want * _t(gy, False)).sum().backward()
+    _close(out, want.detach())
+    _close(gin[0], xt.grad)
+    for i in range(layer_num):
+        _close(gw["kernel%d" % i], ks[i].grad, 2e-4, 2e-5)
+        _close(gw["bias%d" % i], bs[i].grad, 2e-4, 2e-5)
+    with pytest.raises(ValueError):
+        CrossNet(1)(np.zeros((2, 3, 4), np.float32))
+
+
+@pytest.mark.parametrize("layer_size,split_half,act", [((10,), False, "relu"), ((10, 8), True, "relu"),
+                                                       ((10, 8), False, "linear"), ((8, 6, 5), True, "sigmoid")])
+def test_cin(cuda, layer_size, split_half, act):
+    from deepctr_b200.layers import CIN
+    from deepctr_b200 import ops
+    rng = np.random.RandomState(2)
+    B, F, E_ = 37, 4, 3
+    x = rng.normal(size=(B, F, E_)).astype(np.float32)
+    layer = CIN(layer_size, act, split_half, seed=3)
+    layer.build((None, F, E_))
+    for w in layer.weights:
+        w.set_value(rng.normal(0, 0.4, size=w.shape).astype(np.float32))
+    old = ops.CIN_CHUNK_BYTES
+    ops.CIN_CHUNK_BYTES = 4 * E_ * 40 * 11          # force several batch chunks
+    try:
+        out, gy, gin, gw = _run(layer, x, rng)
+    finally:
+        ops.CIN_CHUNK_BYTES = old
+    xt = _t(x)
+    fs = [_t(w.value()) for w in layer.filters]
+    bs = [_t(w.value()) for w in layer.bias]
+    want = O.cin(xt, fs, bs, layer_size, act, split_half)
+    (want * _t(gy, False)).sum().backward()
+    assert out.shape == tuple(want.shape)
+    _close(out, want.detach())
+    _close(gin[0], xt.grad, 3e-4, 3e-5)
+    for i in range(len(layer_size)):
+        _close(gw["filter%d" % i], fs[i].grad, 3e-4, 3e-5)
+        _close(gw["bias%d" % i], bs[i].grad, 3e-4, 3e-5)
+    # closed form of SURVEY.md 8c for the first layer: einsum('bid,bjd,ijn->bdn')
+    W0 = fs[0].detach()[0].reshape(F, F, layer_size[0])
+    y0 = torch.einsum("bid,bjd,ijn->bdn", xt.detach(), xt.detach(), W0) + bs[0].detach()
+    if len(layer_size) == 1:
+        _close(out, O._ACT[act](y0).sum(dim=1))
+    with pytest.raises(ValueError):
+        CIN((3, 4), split_half=True).build((None, 4, 3))   # odd hidden size with split_half
+
+
+@pytest.mark.parametrize("heads,use_res,scaling", [(1, True, False), (2, False, False), (2, True, True)])
+def test_interacting_layer(cuda, heads, use_res, scaling):
+    from deepctr_b200.layers import InteractingLayer
+    rng = np.random.RandomState(3)
+    B, F, E_ = 21, 4, 3
+    x = rng.normal(size=(B, F, E_)).astype(np.float32)
+    layer = InteractingLayer(att_embedding_size=5, head_num=heads, use_res=use_res, scaling=scaling)
+    layer.build((None, F, E_))
+    for w in layer.weights:
+        w.set_value(rng.normal(0, 0.5, size=w.shape).astype(np.float32))
+    out, gy, gin, gw = _run(layer, x, rng)
+    xt = _t(x)
+    wq, wk, wv = _t(layer.W_Query.value()), _t(layer.W_key.value()), _t(layer.W_Value.value())
+    wr = _t(layer.W_Res.value()) if use_res else None
+    want = O.interacting(xt, wq, wk, wv, wr, heads, 5, use_res, scaling)
+    (want * _t(gy, False)).sum().backward()
+    _close(out, want.detach())
+    _close(gin[0], xt.grad, 3e-4, 3e-5)
+    _close(gw["query"], wq.grad, 3e-4, 3e-5)
+    _close(gw["key"], wk.grad, 3e-4, 3e-5)
+    _close(gw["value"], wv.grad, 3e-4, 3e-5)
+    if use_res:
+        _close(gw["res"], wr.grad, 3e-4, 3e-5)
+
+
+@pytest.mark.parametrize("act", ["relu", "sigmoid", "dice"])
+@pytest.mark.parametrize("training", [False, True])
+def test_dnn_layer(cuda, act, training):
+    from deepctr_b200.layers import DNN
+    rng = np.random.RandomState(4)
+    x = rng.normal(size=(65, 9)).astype(np.float32)
+    layer = DNN((7, 5), activation=act, seed=1)
+    layer.build((None, 9))
+    H.randomize_weights(layer, rng, 0.4)
+    out, gy, gin, gw = _run(layer, x, rng, training=training)
+    xt = _t(x)
+    ks = [_t(w.value()) for w in layer.kernels]
+    bs = [_t(w.value()) for w in layer.bias]
+    params = None
+    if act == "dice":
+        # moving statistics were already updated by the training forward: rebuild the pre-step values
+        params = []
+        for al in layer.activation_layers:
+            params.append({"alphas": _t(al.alphas.value()), "moving_mean": _t(al.moving_mean.value(), False),
+                           "moving_var": _t(al.moving_variance.value(), False)})
+        if training:
+            for p in params:       # batch statistics are used in training: moving values are irrelevant
+                p["moving_mean"], p["moving_var"] = None, None
+    want = O.dnn(xt, ks, bs, act, None, params, training)
+    (want * _t(gy, False)).sum().backward()
+    _close(out, want.detach(), 2e-4, 2e-5)
+    _close(gin[0], xt.grad, 5e-4, 5e-5)
+    for i in range(2):
+        _close(gw["kernel%d" % i], ks[i].grad, 5e-4, 5e-5)
+        _close(gw["bias%d" % i], bs[i].grad, 5e-4, 5e-5)
+    if act == "dice":
+        for i, p in enumerate(params):
+            _close(gw["act%d/dice_alpha" % i] if ("act%d/dice_alpha" % i) in gw else
+                   [v for k, v in gw.items() if k.endswith("act%d/dice_alpha" % i)][0], p["alphas"].grad, 5e-4, 5e-5)
+
+
+def test_dice_moving_statistics_update(cuda):
+    from deepctr_b200.layers import Dice
+    rng = np.random.RandomState(5)
+    x = (rng.normal(size=(200, 3)) * 2 + 1).astype(np.float32)
+    layer = Dice()
+    layer.build((None, 3))
+    _run(layer, x, rng, training=True)
+    np.testing.assert_allclose(layer.moving_mean.value(), 0.01 * x.mean(0), rtol=1e-4, atol=1e-6)
+    np.testing.assert_allclose(layer.moving_variance.value(), 0.99 + 0.01 * x.var(0), rtol=1e-4, atol=1e-6)
+
+
+@pytest.mark.parametrize("mode", ["sum", "mean", "max"])
+@pytest.mark.parametrize("masking", [False, True])
+def test_sequence_pooling_layer_standalone(cuda, mode, masking):
+    from deepctr_b200.layers import SequencePoolingLayer
+    from deepctr_b200 import engine as E
+    rng = np.random.RandomState(6)
+    B, T, E_ = 4, 10, 8
+    x = rng.normal(size=(B, T, E_)).astype(np.float32)
+    lens = np.array([[0], [3], [10], [7]], dtype=np.int32)
+    layer = SequencePoolingLayer(mode, supports_masking=masking)
+    if masking:
+        ids = (np.arange(T)[None, :] < lens).astype(np.int32)
+        xv = E.to_var(x)
+        xv.mask = E.KMask(ids=[torch.from_numpy(ids).to(xv.data.device)])
+        out, gy, gin, _ = _run(layer, xv, rng)
+        want_in = dict(mask=torch.from_numpy(ids) != 0)
+    else:
+        out, gy, gin, _ = _run(layer, [x, lens], rng)
+        want_in = dict(lengths=torch.from_numpy(lens.reshape(-1)))
+    xt = _t(x)
+    want = O.sequence_pooling(xt, mode, **want_in)
+    (want * _t(gy, False)).sum().backward()
+    assert np.array_equal(out, want.detach().numpy()), "pooled sums are bit-exact"
+    _close(gin[0], xt.grad)
+
+
+@pytest.mark.parametrize("norm", [True, False])
+def test_weighted_sequence_layer_standalone(cuda, norm):
+    from deepctr_b200.layers import WeightedSequenceLayer
+    rng = np.random.RandomState(7)
+    B, T, E_ = 6, 5, 4
+    x = rng.normal(size=(B, T, E_)).astype(np.float32)
+    w = rng.rand(B, T, 1).astype(np.float32)
+    lens = rng.randint(1, T + 1, size=(B, 1)).astype(np.int32)
+    out, gy, gin, _ = _run(WeightedSequenceLayer(norm), [x, lens, w], rng)
+    xt = _t(x)
+    want = O.weighted_sequence(xt, torch.from_numpy(w), norm, lengths=torch.from_numpy(lens.reshape(-1)))
+    (want * _t(gy, False)).sum().backward()
+    _close(out, want.detach(), 1e-5, 1e-6)
+    _close(gin[0], xt.grad, 1e-5, 1e-6)
+
+
+@pytest.mark.parametrize("weight_normalization", [False, True])
+@pytest.mark.parametrize("act", ["sigmoid", "dice"])
+def test_attention_sequence_pooling_layer(cuda, weight_normalization, act):
+    from deepctr_b200.layers import AttentionSequencePoolingLayer
+    rng = np.random.RandomState(8)
+    B, T, E_ = 4, 10, 8
+    q = rng.normal(size=(B, 1, E_)).astype(np.float32)
+    k = rng.normal(size=(B, T, E_)).astype(np.float32)
+    lens = np.array([[1], [10], [4], [7]], dtype=np.int32)
+    layer = AttentionSequencePoolingLayer((6, 5), act, weight_normalization=weight_normalization)
+    layer.build([(None, 1, E_), (None, T, E_), (None, 1)])
+    H.randomize_weights(layer, rng, 0.4)
+    out, gy, gin, gw = _run(layer, [q, k, lens], rng)
+    qt, kt = _t(q), _t(k)
+    lau = layer.local_att
+    W = {"dnn_kernels": [_t(w.value()) for w in lau.dnn.kernels], "dnn_biases": [_t(w.value()) for w in lau.dnn.bias],
+         "kernel": _t(lau.kernel.value()), "bias": _t(lau.bias.value())}
+    if act == "dice":
+        W["act_params"] = [{"alphas": _t(al.alphas.value()), "moving_mean": _t(al.moving_mean.value(), False),
+                            "moving_var": _t(al.moving_variance.value(), False)} for al in lau.dnn.activation_layers]
+    mask = O.sequence_mask(torch.from_numpy(lens.reshape(-1)), T)
+    want = O.attention_sequence_pooling(qt, kt, mask, W, act, weight_normalization)
+    (want * _t(gy, False)).sum().backward()
+    assert out.shape == (B, 1, E_)
+    _close(out, want.detach(), 2e-4, 2e-5)
+    _close(gin[0], qt.grad, 5e-4, 5e-5)
+    _close(gin[1], kt.grad, 5e-4, 5e-5)
+    _close([v for n, v in gw.items() if n.endswith("local_activation_unit/kernel")][0], W["kernel"].grad, 5e-4, 5e-5)
+    for i in range(2):
+        _close([v for n, v in gw.items() if n.endswith("dnn/kernel%d" % i)][0], W["dnn_kernels"][i].grad, 5e-4, 5e-5)
+    # padded positions receive exactly zero gradient (Appendix F.6)
+    for b in range(B):
+        assert np.all(gin[1][b, lens[b, 0]:] == 0)
+
+
+def test_prediction_and_linear_layers(cuda):
+    from deepctr_b200.layers import PredictionLayer, Linear
+    rng = np.random.RandomState(9)
+    z = rng.normal(size=(50, 1)).astype(np.float32)
+    for task in ["binary", "regression"]:
+        layer = PredictionLayer(task)
+        layer.build((None, 1))
+        layer.global_bias.set_value(np.array([0.25], np.float32))
+        got = layer(z)
+        want = O.prediction(torch.from_numpy(z), torch.tensor([0.25]), task)
+        _close(got.data.cpu().numpy(), want.numpy(), 1e-5, 1e-6)
+    with pytest.raises(ValueError):
+        PredictionLayer("ranking")
+    with pytest.raises(ValueError):
+        Linear(mode=3)
+    sp = rng.normal(size=(20, 1, 6)).astype(np.float32)
+    dn = rng.normal(size=(20, 4)).astype(np.float32)
+    lin = Linear(mode=2, use_bias=True)
+    lin.build([(None, 1, 6), (None, 4)])
+    lin.kernel.set_value(rng.normal(size=(4, 1)).astype(np.float32))
+    lin.bias.set_value(np.array([0.5], np.float32))
+    got = lin([sp, dn]).data.cpu().numpy()
+    want = O.linear(torch.from_numpy(sp), torch.from_numpy(dn), torch.from_numpy(lin.kernel.value()),
+                    torch.tensor([0.5]))
+    _close(got, want.numpy())
+
+
+def test_hash_layer_device_and_vocabulary(cuda, tmp_path):
+    from deepctr_b200.layers import Hash
+    ids = np.array([[0], [1], [12345], [99999999]], dtype=np.int32)
+    for mz in (False, True):
+        got = Hash(100, mask_zero=mz)(ids).data.cpu().numpy()
+        assert np.array_equal(got, O.hash_layer(ids, 100, mz))
+    # the reference's only known-answer vector (tests/layers/utils_test.py:20-22)
+    p = tmp_path / "vocab.csv"
+    p.write_text("1,lake\n2,merson\n3,johnson\n")
+    out = Hash(num_buckets=4, vocabulary_path=str(p))([["lake"], ["johnson"], ["lakemerson"]])
+    assert np.array_equal(np.asarray(out), [[1], [3], [0]])

@@ -488,10 +488,10 @@ class EmbeddingPlanner(object):
             K.embed_gather_fwd(feats, batch)
         # ---- hand the windows to the graph executor ---------------------------------------------------
         from . import ops
+        vlin = E.Var(None, owner=self, name="__virtual_lin__")   # virtual: only its row-sum exists this step
         for s in self.slots:
             if s.buf == "lin" and lin_fused:
-                base = E.Var(None, owner=self)       # virtual: only its row-sum exists this step
-                base.name = "__virtual_lin__"
+                base = vlin
                 out = E.Var(None, base=base, col0=s.col, ncols=s.dim, owner=self, vshape=(batch, 1, s.dim))
             elif s.buf == "seq":
                 base = bufs[id(s)]

@@ -48,6 +48,13 @@ class DNN(Layer):
         self.activation_layers = [None if (fusable_activation(a) and not self.use_bn)
                                   else self._track(activation_layer(a, name=self.name + "/act%d" % i))
                                   for i, a in enumerate(self.act_names)]
+        # build sub-layers now so that their weights exist (get_weights / set_weights) before the first call
+        for i in range(len(self.hidden_units)):
+            shape = tuple(input_shape[:-1]) + (int(self.hidden_units[i]),)
+            if self.use_bn:
+                self.bn_layers[i]._maybe_build(shape)
+            if self.activation_layers[i] is not None:
+                self.activation_layers[i]._maybe_build(shape)
         self.built = True
 
     def call(self, inputs, training=None, **kwargs):

@@ -9,23 +9,39 @@ namespace b2ctr {
 // dz = dy * act'(y);  dbias = column sums of dz  (two deterministic passes: per-block partial
 // sums over a fixed row range, then a fixed-order reduction over blocks)
 // -------------------------------------------------------------------------------------------
-constexpr int kBiasRowsPerBlock = 256;
+constexpr int kBiasRowsPerBlock = 128;
 
+// block = 8 warps; warp w owns rows r0 + w, r0 + w + 8, ...; lanes own 32 consecutive columns (coalesced);
+// the 8 per-warp partials are combined through shared memory in a fixed order.
 __global__ void __launch_bounds__(256)
     bias_act_bwd_kernel(const float* __restrict__ dy, const float* __restrict__ y, float* dz,
                         float* partial, int64_t m, int64_t n, int64_t ld, int act) {
-  // block handles rows [r0, r0+kBiasRowsPerBlock) and all columns (strided by 256 threads... per column)
+  __shared__ float red[8][33];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int64_t r0 = (int64_t)blockIdx.x * kBiasRowsPerBlock;
   const int64_t r1 = r0 + kBiasRowsPerBlock < m ? r0 + kBiasRowsPerBlock : m;
-  for (int64_t c = threadIdx.x; c < n; c += blockDim.x) {
+  for (int64_t c0 = 0; c0 < n; c0 += 32) {
+    const int64_t c = c0 + lane;
     float s = 0.f;
-    for (int64_t r = r0; r < r1; ++r) {
-      const int64_t o = r * ld + c;
-      const float g = dy[o] * (act == B2CTR_ACT_NONE ? 1.f : act_grad_from_out(y[o], act));
-      if (dz) dz[o] = g;
-      s += g;
+    if (c < n) {
+      for (int64_t r = r0 + warp; r < r1; r += 8) {
+        const int64_t o = r * ld + c;
+        const float g = dy[o] * (act == B2CTR_ACT_NONE ? 1.f : act_grad_from_out(y[o], act));
+        if (dz) dz[o] = g;
+        s += g;
+      }
     }
-    if (partial) partial[(int64_t)blockIdx.x * n + c] = s;
+    if (partial) {
+      red[warp][lane] = s;
+      __syncthreads();
+      if (warp == 0 && c < n) {
+        float t = 0.f;
+#pragma unroll
+        for (int w = 0; w < 8; ++w) t += red[w][lane];
+        partial[(int64_t)blockIdx.x * n + c] = t;
+      }
+      __syncthreads();
+    }
   }
 }
 __global__ void bias_reduce_kernel(const float* __restrict__ partial, float* dbias, int64_t nblocks,

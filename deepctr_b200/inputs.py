@@ -742,6 +742,27 @@ class Feeder(object):
                 continue
             b = items[0][1].shape[0]
             total = sum(w for _, _, w in items)
+            if key != "f32":
+                # ids: one flat staging buffer of per-input contiguous blocks (a plain memcpy per input on
+                # the host, one H2D for all); the gather kernels take a pointer + stride per feature
+                stage = self._stage(key, (b * total,), th_dt[key])
+                sn = stage.numpy()
+                off = 0
+                for name, a, w in items:
+                    sn[off:off + b * w].reshape(b, w)[...] = a
+                    off += b * w
+                pack = stage.to(dev, non_blocking=True)
+                self._copied()
+                self.h2d_bytes += stage.numel() * stage.element_size()
+                off = 0
+                for name, a, w in items:
+                    spec = self.specs[name]
+                    shape = (b,) + tuple(int(s) for s in spec.shape[1:])
+                    v = E.Var(pack[off:off + b * w].reshape(shape))
+                    v.name = name
+                    feed[name] = v
+                    off += b * w
+                continue
             stage = self._stage(key, (b, total), th_dt[key])
             sn = stage.numpy()
             col = 0

@@ -44,13 +44,60 @@ __global__ void __launch_bounds__(256)
     }
   }
 }
-__global__ void bias_reduce_kernel(const float* __restrict__ partial, float* dbias, int64_t nblocks,
-                                   int64_t n) {
-  const int64_t c = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (c >= n) return;
+// float4 variant for n % 4 == 0 with (n/4) dividing 256: thread -> (row group, 4-column group); the
+// row groups are combined through shared memory in a fixed order.
+__global__ void __launch_bounds__(256)
+    bias_act_bwd_vec4_kernel(const float* __restrict__ dy, const float* __restrict__ y, float* dz,
+                             float* partial, int64_t m, int64_t n, int64_t ld, int act) {
+  __shared__ float4 red[256];
+  const int cgs = (int)(n >> 2);              // column groups
+  const int rgs = 256 / cgs;                  // row groups per pass
+  const int cg = threadIdx.x % cgs, rg = threadIdx.x / cgs;
+  const int64_t r0 = (int64_t)blockIdx.x * kBiasRowsPerBlock;
+  const int64_t r1 = r0 + kBiasRowsPerBlock < m ? r0 + kBiasRowsPerBlock : m;
+  float4 s = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll 4
+  for (int64_t r = r0 + rg; r < r1; r += rgs) {
+    const int64_t o = r * ld + cg * 4;
+    float4 g = *reinterpret_cast<const float4*>(dy + o);
+    if (act != B2CTR_ACT_NONE) {
+      const float4 yy = *reinterpret_cast<const float4*>(y + o);
+      g.x *= act_grad_from_out(yy.x, act); g.y *= act_grad_from_out(yy.y, act);
+      g.z *= act_grad_from_out(yy.z, act); g.w *= act_grad_from_out(yy.w, act);
+    }
+    if (dz) *reinterpret_cast<float4*>(dz + o) = g;
+    s.x += g.x; s.y += g.y; s.z += g.z; s.w += g.w;
+  }
+  if (partial) {
+    red[threadIdx.x] = s;
+    __syncthreads();
+    if (rg == 0) {
+      float4 t = red[cg];
+      for (int k = 1; k < rgs; ++k) {
+        const float4 v = red[k * cgs + cg];
+        t.x += v.x; t.y += v.y; t.z += v.z; t.w += v.w;
+      }
+      *reinterpret_cast<float4*>(partial + (int64_t)blockIdx.x * n + cg * 4) = t;
+    }
+  }
+}
+// one block per 32 columns; 8 warps stride the partial blocks, combined in a fixed order
+__global__ void __launch_bounds__(256)
+    bias_reduce_kernel(const float* __restrict__ partial, float* dbias, int64_t nblocks, int64_t n) {
+  __shared__ float red[8][33];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int64_t c = (int64_t)blockIdx.x * 32 + lane;
   float s = 0.f;
-  for (int64_t b = 0; b < nblocks; ++b) s += partial[b * n + c];
-  dbias[c] = s;
+  if (c < n)
+    for (int64_t b = warp; b < nblocks; b += 8) s += partial[b * n + c];
+  red[warp][lane] = s;
+  __syncthreads();
+  if (warp == 0 && c < n) {
+    float t = 0.f;
+#pragma unroll
+    for (int w = 0; w < 8; ++w) t += red[w][lane];
+    dbias[c] = t;
+  }
 }
 
 __global__ void act_fwd_kernel(const float* __restrict__ x, float* y, int64_t n, int act) {
@@ -283,12 +330,19 @@ b2ctr_status_t b2ctr_bias_act_bwd(const float* dy, const float* y, float* dz, fl
       return B2CTR_ERR_WORKSPACE;
     }
   }
-  bias_act_bwd_kernel<<<(unsigned)nblocks, 256, 0, ST>>>(dy, y, dz, dbias ? (float*)workspace : nullptr,
-                                                        m, n, ld, act);
+  const bool vec = n % 4 == 0 && n / 4 <= 256 && 256 % (n / 4) == 0 && ld % 4 == 0 &&
+                   ((uintptr_t)dy & 15) == 0 && (!y || ((uintptr_t)y & 15) == 0) &&
+                   (!dz || ((uintptr_t)dz & 15) == 0);
+  if (vec)
+    bias_act_bwd_vec4_kernel<<<(unsigned)nblocks, 256, 0, ST>>>(dy, y, dz, dbias ? (float*)workspace : nullptr,
+                                                               m, n, ld, act);
+  else
+    bias_act_bwd_kernel<<<(unsigned)nblocks, 256, 0, ST>>>(dy, y, dz, dbias ? (float*)workspace : nullptr,
+                                                          m, n, ld, act);
   B2_CHECK_LAUNCH("b2ctr_bias_act_bwd");
   if (dbias) {
-    bias_reduce_kernel<<<(unsigned)ceil_div(n, 128), 128, 0, ST>>>((const float*)workspace, dbias,
-                                                                  nblocks, n);
+    bias_reduce_kernel<<<(unsigned)ceil_div(n, 32), 256, 0, ST>>>((const float*)workspace, dbias,
+                                                                 nblocks, n);
     B2_CHECK_LAUNCH("b2ctr_bias_act_bwd(reduce)");
   }
   return B2CTR_OK;

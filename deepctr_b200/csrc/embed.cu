@@ -398,31 +398,35 @@ __device__ __forceinline__ int64_t uni_id(const UniParams& p, int f, int64_t b) 
   return load_idx(p.idx[f], b * p.idx_stride[f], p.idx_dtype);
 }
 
-// LPR = lanes per row (= dim/4); RPI = rows per warp iteration; each lane keeps U loads in flight.
+// LPR = lanes per row (= dim/4); RPI = rows per warp iteration; each lane keeps U 16-byte loads in flight.
+// Latency hiding (ncu, profiles/r1_embed_before.txt: 40 % DRAM, 35 % warps active): the id -> row -> store
+// chain is broken by prefetching the NEXT sample's ids before the current rows are requested, and the
+// register budget is capped at 64 (4 CTAs = 32 warps per SM).
 template <int LPR>
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(256, 4)
     gather_uniform_fwd_kernel(const __grid_constant__ UniParams p, int64_t batch) {
   constexpr int RPI = 32 / LPR;
-  constexpr int U = 8;
+  constexpr int U = 7;   // 7 x RPI(4) = 28 >= 26 Criteo fields in one pass at dim 32
   const int lane = threadIdx.x & 31;
   const int slot = lane / LPR, chunk = lane % LPR;
   const int F = p.nfeat, dim = p.dim;
   const int64_t nwarps = (int64_t)gridDim.x * (blockDim.x >> 5);
-  for (int64_t b = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); b < batch;
-       b += nwarps) {
-    // ids: lane l holds features l and l+32 (coalesced when the ids form a [B,F] matrix)
-    int64_t id0 = lane < F ? uni_id(p, lane, b) : 0;
-    int64_t id1 = lane + 32 < F ? uni_id(p, lane + 32, b) : 0;
+  int64_t b = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  // ids: lane l holds features l and l+32
+  int64_t id0 = (b < batch && lane < F) ? uni_id(p, lane, b) : 0;
+  int64_t id1 = (b < batch && lane + 32 < F) ? uni_id(p, lane + 32, b) : 0;
+  for (; b < batch; b += nwarps) {
+    const int64_t bn = b + nwarps;
+    const int64_t nid0 = (bn < batch && lane < F) ? uni_id(p, lane, bn) : 0;        // prefetch
+    const int64_t nid1 = (bn < batch && lane + 32 < F) ? uni_id(p, lane + 32, bn) : 0;
     float* xrow = p.x + b * p.ldx;
     float4 s = make_float4(0.f, 0.f, 0.f, 0.f);
     float q = 0.f;
     for (int f0 = 0; f0 < F; f0 += U * RPI) {
       float4 v[U];
-      int fi[U];
 #pragma unroll
       for (int u = 0; u < U; ++u) {
         const int f = f0 + u * RPI + slot;
-        fi[u] = f;
         const int fs = f < F ? f : 0;
         const int64_t ida = __shfl_sync(0xffffffffu, id0, fs & 31);
         const int64_t idb = __shfl_sync(0xffffffffu, id1, fs & 31);
@@ -431,7 +435,7 @@ __global__ void __launch_bounds__(256)
       }
 #pragma unroll
       for (int u = 0; u < U; ++u) {
-        const int f = fi[u];
+        const int f = f0 + u * RPI + slot;
         if (f < F) {
           stg_stream_f4(xrow + (int64_t)f * dim + chunk * 4, v[u]);
           if ((p.fm_mask >> f) & 1ull) {
@@ -464,40 +468,53 @@ __global__ void __launch_bounds__(256)
       l = warp_sum(l);
       if (lane == 0) p.linear[b] = l;
     }
-    // dense passthrough + zero padding up to ldx (so x is directly the K-padded GEMM operand)
+    // dense passthrough + zero padding up to x_cols (so x is directly the K-padded GEMM operand)
     const int64_t c0 = (int64_t)F * dim;
     for (int64_t c = c0 + lane; c < p.x_cols; c += 32) {
       const int j = (int)(c - c0);
       xrow[c] = j < p.ndense ? p.dense[b * p.dense_ld + j] : 0.f;
     }
+    id0 = nid0;
+    id1 = nid1;
   }
 }
 
+// Backward: 4 dx + 4 x loads in flight per lane, reds issued as soon as a chunk's gradient is formed
+// (fire-and-forget), ids re-broadcast by shuffle instead of being kept in registers -> 64 registers.
 template <int LPR>
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(256, 3)
     scatter_uniform_bwd_kernel(const __grid_constant__ UniParams p, const float* __restrict__ dx,
                                const float* __restrict__ dfm, const float* __restrict__ dlinear,
                                float scale, float lin_scale, int64_t batch) {
   constexpr int RPI = 32 / LPR;
-  constexpr int U = 8;
+  constexpr int U = 4;
   const int lane = threadIdx.x & 31;
   const int slot = lane / LPR, chunk = lane % LPR;
   const int F = p.nfeat, dim = p.dim;
   const int64_t nwarps = (int64_t)gridDim.x * (blockDim.x >> 5);
-  for (int64_t b = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); b < batch;
-       b += nwarps) {
-    int64_t id0 = lane < F ? uni_id(p, lane, b) : 0;
-    int64_t id1 = lane + 32 < F ? uni_id(p, lane + 32, b) : 0;
+  int64_t b = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  int64_t id0 = (b < batch && lane < F) ? uni_id(p, lane, b) : 0;
+  int64_t id1 = (b < batch && lane + 32 < F) ? uni_id(p, lane + 32, b) : 0;
+  for (; b < batch; b += nwarps) {
+    const int64_t bn = b + nwarps;
+    const int64_t nid0 = (bn < batch && lane < F) ? uni_id(p, lane, bn) : 0;
+    const int64_t nid1 = (bn < batch && lane + 32 < F) ? uni_id(p, lane + 32, bn) : 0;
     const float* xrow = p.x + b * p.ldx;
     const float* dxrow = dx ? dx + b * p.ldx : nullptr;
     const float gfm = dfm ? dfm[b] : 0.f;
     float4 s = make_float4(0.f, 0.f, 0.f, 0.f);
     if (dfm) {
-      for (int f = slot; f < F; f += RPI) {
-        if ((p.fm_mask >> f) & 1ull) {
-          const float4 v = *reinterpret_cast<const float4*>(xrow + (int64_t)f * dim + chunk * 4);
-          s.x += v.x; s.y += v.y; s.z += v.z; s.w += v.w;
+      for (int f0 = 0; f0 < F; f0 += U * RPI) {
+        float4 v[U];
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+          const int f = f0 + u * RPI + slot;
+          v[u] = make_float4(0.f, 0.f, 0.f, 0.f);
+          if (f < F && ((p.fm_mask >> f) & 1ull))
+            v[u] = *reinterpret_cast<const float4*>(xrow + (int64_t)f * dim + chunk * 4);
         }
+#pragma unroll
+        for (int u = 0; u < U; ++u) { s.x += v[u].x; s.y += v[u].y; s.z += v[u].z; s.w += v[u].w; }
       }
 #pragma unroll
       for (int o = LPR; o < 32; o <<= 1) {
@@ -508,34 +525,35 @@ __global__ void __launch_bounds__(256)
       }
     }
     for (int f0 = 0; f0 < F; f0 += U * RPI) {
-      float4 g[U];
-      int64_t ids[U];
+      float4 g[U], xv[U];
+#pragma unroll
+      for (int u = 0; u < U; ++u) {
+        const int f = f0 + u * RPI + slot;
+        g[u] = make_float4(0.f, 0.f, 0.f, 0.f);
+        xv[u] = g[u];
+        if (f < F) {
+          const int64_t off = (int64_t)f * dim + chunk * 4;
+          if (dxrow) g[u] = ldg_stream_f4(dxrow + off);
+          if (dfm && ((p.fm_mask >> f) & 1ull)) xv[u] = *reinterpret_cast<const float4*>(xrow + off);  // L1 hit
+        }
+      }
 #pragma unroll
       for (int u = 0; u < U; ++u) {
         const int f = f0 + u * RPI + slot;
         const int fs = f < F ? f : 0;
         const int64_t ida = __shfl_sync(0xffffffffu, id0, fs & 31);
         const int64_t idb = __shfl_sync(0xffffffffu, id1, fs & 31);
-        ids[u] = fs < 32 ? ida : idb;
-        g[u] = make_float4(0.f, 0.f, 0.f, 0.f);
+        const int64_t id = fs < 32 ? ida : idb;
         if (f < F) {
-          const int64_t off = (int64_t)f * dim + chunk * 4;
-          if (dxrow) g[u] = ldg_stream_f4(dxrow + off);
+          float4 r = g[u];
           if (dfm && ((p.fm_mask >> f) & 1ull)) {
-            const float4 v = *reinterpret_cast<const float4*>(xrow + off);
-            g[u].x += gfm * (s.x - v.x);
-            g[u].y += gfm * (s.y - v.y);
-            g[u].z += gfm * (s.z - v.z);
-            g[u].w += gfm * (s.w - v.w);
+            r.x += gfm * (s.x - xv[u].x);
+            r.y += gfm * (s.y - xv[u].y);
+            r.z += gfm * (s.z - xv[u].z);
+            r.w += gfm * (s.w - xv[u].w);
           }
-        }
-      }
-#pragma unroll
-      for (int u = 0; u < U; ++u) {
-        const int f = f0 + u * RPI + slot;
-        if (f < F) {
-          g[u].x *= scale; g[u].y *= scale; g[u].z *= scale; g[u].w *= scale;
-          red_add_f4(p.table[f] + ids[u] * dim + chunk * 4, g[u]);
+          r.x *= scale; r.y *= scale; r.z *= scale; r.w *= scale;
+          red_add_f4(p.table[f] + id * dim + chunk * 4, r);
         }
       }
     }
@@ -544,6 +562,8 @@ __global__ void __launch_bounds__(256)
       if (lane < F) red_add_f1(p.lin[lane] + id0, gl);
       if (lane + 32 < F) red_add_f1(p.lin[lane + 32] + id1, gl);
     }
+    id0 = nid0;
+    id1 = nid1;
   }
 }
 

@@ -274,7 +274,10 @@ def predict_loss(logit, bias=None, labels=None, task=L.TASK_BINARY, want_grad=Fa
     batch = logit.numel()
     pred = torch.empty((batch,), dtype=torch.float32, device=logit.device)
     dlogit = torch.empty((batch,), dtype=torch.float32, device=logit.device) if want_grad else None
-    acc = torch.zeros((2,), dtype=torch.float32, device=logit.device) if labels is not None else None
+    acc = None
+    if labels is not None:
+        acc = torch.empty((2,), dtype=torch.float32, device=logit.device)
+        fill(acc, 0.0)
     loss_sum = acc[0:1] if acc is not None else None
     dbias = acc[1:2] if (acc is not None and want_grad and bias is not None) else None
     L.check(L.lib().b2ctr_predict_loss(ptr(logit), ptr(bias), ptr(labels), ptr(pred), ptr(dlogit),

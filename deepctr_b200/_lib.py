@@ -121,6 +121,11 @@ SIGNATURES = {
     "b2ctr_dice_bwd_workspace_bytes": (_sz, [_i64, _i64]),
     "b2ctr_dice_bwd": (_i32, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _i64, _i64, _f32, _i32, _vp, _sz, _vp]),
     "b2ctr_dropout": (_i32, [_vp, _vp, _i64, _f32, _u64, _vp]),
+    "b2ctr_shard_bucketize": (_i32, [C.POINTER(Feature), _i32, _i64, _i32, _vp, _vp, _vp]),
+    "b2ctr_shard_fill": (_i32, [C.POINTER(Feature), _i32, _i64, _i32, _vp, _vp, _vp, _vp, _vp]),
+    "b2ctr_shard_gather_rows": (_i32, [C.POINTER(_vp), C.POINTER(_vp), _i32, _i32, _vp, _i64, _vp, _vp, _vp]),
+    "b2ctr_shard_scatter_rows": (_i32, [C.POINTER(_vp), C.POINTER(_vp), _i32, _i32, _vp, _i64, _vp, _vp, _f32,
+                                        _f32, _vp]),
 }
 
 

@@ -18,6 +18,7 @@
 //                x 3 split terms per stage, then tcgen05.commit to release the stage / publish the tile.
 // Stages: kStages x (A hi+lo 32 KB + B hi+lo BN*256 B).  TMEM: BN fp32 columns x 128 lanes.
 #include <cuda_bf16.h>
+#include <stdlib.h>
 #include "common.cuh"
 
 namespace b2ctr {
@@ -129,7 +130,7 @@ __device__ __forceinline__ void produce_chunk(const float* __restrict__ base, in
 }
 
 template <int BN, int STAGES, bool A_KC, bool B_KC>
-__global__ void __launch_bounds__(kTcThreads, 1) gemm_bf16x3_kernel(const TcArgs g) {
+__global__ void __launch_bounds__(kTcThreads, STAGES == 1 ? 3 : 1) gemm_bf16x3_kernel(const TcArgs g) {
   constexpr int A_PLANE = kTM * 128;       // bytes of one bf16 plane of the A tile (128 rows x 64 k)
   constexpr int B_PLANE = BN * 128;
   constexpr int STAGE = 2 * A_PLANE + 2 * B_PLANE;
@@ -361,9 +362,23 @@ b2ctr_status_t gemm_bf16x3(const b2ctr_gemm_t* g, void* workspace, size_t worksp
   const bool akc = !g->trans_a;   // A stored [M,K]: K contiguous
   const bool bkc = g->trans_b != 0;  // B stored [N,K]: K contiguous
   cudaError_t e;
-  if (g->n <= 32) e = launch_tc<32, 4>(ta, akc, bkc, st);
-  else if (g->n <= 64) e = launch_tc<64, 4>(ta, akc, bkc, st);
-  else e = launch_tc<128, 3>(ta, akc, bkc, st);
+  // Two pipeline shapes: (a) deep intra-CTA pipeline, 1 CTA per SM; (b) single stage, 3 CTAs per SM, so the
+  // global-load latency of one CTA's producers overlaps the convert / MMA phases of its neighbours.
+  // (b) wins for these producer-bound shapes (profiles/r1_gemm_tc.txt); B2CTR_TC_STAGES overrides.
+  static int stages_mode = -1;
+  if (stages_mode < 0) {
+    const char* ev = getenv("B2CTR_TC_STAGES");
+    stages_mode = ev ? atoi(ev) : 1;
+  }
+  if (stages_mode == 1) {
+    if (g->n <= 32) e = launch_tc<32, 1>(ta, akc, bkc, st);
+    else if (g->n <= 64) e = launch_tc<64, 1>(ta, akc, bkc, st);
+    else e = launch_tc<128, 1>(ta, akc, bkc, st);
+  } else {
+    if (g->n <= 32) e = launch_tc<32, 4>(ta, akc, bkc, st);
+    else if (g->n <= 64) e = launch_tc<64, 4>(ta, akc, bkc, st);
+    else e = launch_tc<128, 3>(ta, akc, bkc, st);
+  }
   if (e != cudaSuccess) {
     set_error("b2ctr_gemm(bf16x3): CUDA launch failed: %s", cudaGetErrorString(e));
     return B2CTR_ERR_CUDA;

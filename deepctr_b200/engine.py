@@ -402,9 +402,12 @@ class Weight(Var):
         elif (isinstance(self.initializer, RandomNormal) and type(self.initializer) is RandomNormal
               and self.numel() >= _DEVICE_INIT_THRESHOLD):
             self.data = torch.empty(self.shape_, dtype=torch.float32, device=dev)
+            import zlib
             seed = self.initializer.seed if self.initializer.seed is not None else 0
+            shard = self.opt_state.get("shard", (0, 1, 0))[0]
             K.init_normal(self.data, self.initializer.mean, self.initializer.stddev,
-                          (seed * 0x9E3779B97F4A7C15 + hash(self.name)) & 0xFFFFFFFFFFFFFFFF)
+                          (seed * 0x9E3779B97F4A7C15 + zlib.crc32(self.name.encode()) * 1000003 + shard)
+                          & 0xFFFFFFFFFFFFFFFF)
         else:
             self.data = torch.from_numpy(self.initializer.host(self.shape_)).to(dev)
         return self.data
@@ -904,7 +907,8 @@ class Model(object):
         print_fn("Total params: %d" % self.count_params())
 
     # ---- execution ---------------------------------------------------------------------------
-    def compile(self, optimizer="adam", loss=None, metrics=None, embedding_update="auto", **kw):
+    def compile(self, optimizer="adam", loss=None, metrics=None, embedding_update="auto", distributed="auto",
+                **kw):
         """``embedding_update``: 'dense' = Keras semantics (dense gradient + dense optimizer + l2 on
         the whole table; O(vocab) per step), 'sparse' = fused row-wise SGD scatter
         (O(batch); l2 on tables must be 0), 'auto' = dense below 4M table elements."""
@@ -915,6 +919,14 @@ class Model(object):
         if embedding_update not in ("auto", "dense", "sparse"):
             raise ValueError("embedding_update must be auto / dense / sparse")
         self.planner.configure(self.optimizer, embedding_update)
+        # multi-GPU (one process per GPU): dense weights data-parallel, fast-path tables row-sharded
+        self.dist = None
+        if distributed not in (None, False):
+            import torch.distributed as tdist
+            if tdist.is_available() and tdist.is_initialized() and tdist.get_world_size() > 1:
+                from . import parallel
+                self.dist = parallel.DistContext()
+                self.planner.set_dist(self.dist)
 
     def _materialize(self):
         for w in self.weights:
@@ -1008,9 +1020,16 @@ class Model(object):
             self.optimizer.iterations += 1
             tape.ctx["optimizer"] = self.optimizer
             tape.backward()
-            for w in self.trainable_weights:
-                if not w.sparse_grad:
-                    self.optimizer.apply(w)
+            dense = [w for w in self.trainable_weights if not w.sparse_grad]
+            if getattr(self, "dist", None) is not None:
+                from . import parallel
+                parallel.reduce_dense_grads(
+                    self.dist, dense,
+                    lambda src, flat, off: K.copy2d(src.reshape(1, -1), src.numel(), flat, flat.numel(), 1,
+                                                    src.numel(), dst_off=off),
+                    lambda flat, f: K.add_n([flat], scales=[f], out=flat))
+            for w in dense:
+                self.optimizer.apply(w)
         return loss_sum, pred, lt.shape[0]
 
     def train_step(self, x, y):

@@ -393,6 +393,38 @@ class EmbeddingPlanner(object):
             if isinstance(l, Embedding):
                 l.embeddings.sparse_grad = bool(sparse and l.embeddings.trainable)
 
+    def set_dist(self, ctx):
+        """Row-shard the fast-path tables (and their dim-1 linear twins) over the process group:
+        row r -> rank r % world, local row r // world.  Everything else stays replicated."""
+        from . import parallel
+        self.dist = ctx
+        self.exchange = parallel.ShardedExchange(ctx, K)
+        self.sharded = False
+        if not self.fast or ctx.world == 1:
+            return
+        lin_ok = self._lin_matches_fast()
+        if self.lin and not lin_ok:
+            return        # unusual graph: keep the tables replicated (dense gradients are all-reduced)
+        if self.optimizer is None or self.optimizer.name != "sgd":
+            raise ValueError("row-sharded embeddings need the 'sgd' optimizer (fused row-wise update)")
+        seen = set()
+        for s_ in list(self.main[:self.fast_n]) + (list(self.lin) if lin_ok else []):
+            w = s_.emb.embeddings
+            if id(w) in seen:
+                continue
+            seen.add(id(w))
+            full_v = w.shape_[0]
+            if w.data is not None or w.host_value is not None:
+                full = w.value()
+                w.data = None
+                w.host_value = np.ascontiguousarray(parallel.shard_rows(full, ctx.rank, ctx.world))
+            w.shape_ = (parallel.shard_size(full_v, ctx.rank, ctx.world),) + tuple(w.shape_[1:])
+            w.opt_state["shard"] = (ctx.rank, ctx.world, full_v)
+            w.sparse_grad = bool(w.trainable)
+        self.sharded = True
+        if lin_ok:
+            self.lin_hint = True     # the linear rows never leave their owner: only the per-sample sum exists
+
     def _fast_eligible(self):
         m = self.main
         if not m or len(m) > 64:
@@ -453,8 +485,24 @@ class EmbeddingPlanner(object):
         plan = None
         if fast_slots:
             x = bufs["main"].data
-            feats = [self._feature(s, feed, x, self.main_ld) for s in fast_slots]
-            lin_tabs = [s.emb.embeddings.materialize().reshape(-1) for s in self.lin] if lin_fused else None
+            self.route = None
+            if getattr(self, "sharded", False):
+                # ids -> owners (all-to-all), rows -> back (all-to-all); the returned row buffer then plays
+                # the role of the table and `pos` the role of the ids for the ordinary fused gather
+                id_feats = [self._feature(s, feed, x, self.main_ld) for s in fast_slots]
+                st = self.exchange.route(id_feats, batch)
+                dimf = fast_slots[0].dim
+                tabs = [s.emb.embeddings.materialize() for s in fast_slots]
+                ltabs = [s.emb.embeddings.materialize().reshape(-1) for s in self.lin] if lin_fused else None
+                rows, rlin = self.exchange.fetch(st, tabs, ltabs, dimf)
+                self.route = (st, tabs, ltabs, dimf)
+                pos = st["pos"]
+                feats = [K.make_feature(rows, pos[:, f], x, out_col=s.col, out_ld=self.main_ld)
+                         for f, s in enumerate(fast_slots)]
+                lin_tabs = [rlin] * len(fast_slots) if lin_fused else None
+            else:
+                feats = [self._feature(s, feed, x, self.main_ld) for s in fast_slots]
+                lin_tabs = [s.emb.embeddings.materialize().reshape(-1) for s in self.lin] if lin_fused else None
             only_fast = len(self.main) == self.fast_n
             dense = None
             if only_fast and self.tail_hint is not None and "__dense_pack__" in feed:
@@ -547,7 +595,30 @@ class EmbeddingPlanner(object):
             dx = main.grad
             dfm = self.fm_result[1].grad if self.fm_result is not None else None
             dlin = self.lin_result.grad if self.lin_result is not None else None
-            if dx is not None or dfm is not None or dlin is not None:
+            if (dx is not None or dfm is not None or dlin is not None) and getattr(self, "route", None) is not None:
+                # sharded: gradient rows are formed in request order, return to their owners over NVLink
+                # and are applied there by the fused SGD scatter (scale = -lr / world: global-batch mean)
+                st, tabs, ltabs, dimf = self.route
+                dev = main.data.device
+                grows = torch.empty((st["n_send"], dimf), dtype=torch.float32, device=dev)
+                K.fill(grows, 0.0)
+                glin = None
+                if lin_fused:
+                    glin = torch.empty((st["n_send"],), dtype=torch.float32, device=dev)
+                    K.fill(glin, 0.0)
+                pos = st["pos"]
+                feats = [K.make_feature(grows, pos[:, f], main.data, out_col=s.col, out_ld=self.main_ld)
+                         for f, s in enumerate(fast_slots)]
+                bplan = K.UniformPlan(feats, [glin] * len(fast_slots) if lin_fused else None, None, main.data,
+                                      None, None, plan.g.fm_mask[0])
+                bplan.g.x_cols = plan.g.x_cols
+                K.embed_scatter_uniform_bwd(bplan, dx, None if dfm is None else dfm.reshape(-1).contiguous(),
+                                            None if dlin is None else dlin.reshape(-1).contiguous(),
+                                            1.0, 1.0, batch)
+                lr = opt["optimizer"].lr if opt and opt.get("optimizer") else 0.0
+                sc = -lr / self.dist.world
+                self.exchange.push(st, tabs, ltabs, dimf, grows, glin, sc, sc)
+            elif dx is not None or dfm is not None or dlin is not None:
                 tgts = [self._target(s.emb.embeddings, opt) for s in fast_slots]
                 feats = [self._feature(s, feed, main.data, self.main_ld, table=tgt)
                          for s, (tgt, _) in zip(fast_slots, tgts)]

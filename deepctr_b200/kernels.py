@@ -521,3 +521,47 @@ for _n in ("ewise", "cross_vector_fwd", "cross_vector_bwd", "cin_outer_fwd", "ci
            "din_pool_fwd", "din_pool_bwd", "seqpool_fwd", "seqpool_bwd", "seqweight", "seqscale", "colstats",
            "bn_apply", "bn_bwd", "dice_fwd", "dice_bwd", "dropout"):
     globals()[_n] = _timed(globals()[_n])
+
+
+# ---- row-sharded embedding exchange (device side) ----------------------------------------------------
+def shard_bucketize(feats, batch, world):
+    """-> (counts int32 [world], slot int64 [B*F]) for the lookups described by feats[f].idx."""
+    dev = torch.device("cuda", torch.cuda.current_device())
+    counts = torch.empty((world,), dtype=torch.int32, device=dev)
+    fill(counts.view(torch.float32), 0.0)
+    slot = torch.empty((batch * len(feats),), dtype=torch.int64, device=dev)
+    arr = _feat_array(feats)
+    _lib_call("shard_bucketize", arr, len(feats), batch, world, ptr(counts), ptr(slot), stream())
+    return counts, slot
+
+
+def shard_fill(feats, batch, world, counts, slot):
+    dev = counts.device
+    n = batch * len(feats)
+    keys = torch.empty((n,), dtype=torch.int64, device=dev)
+    pos = torch.empty((batch, len(feats)), dtype=torch.int32, device=dev)
+    arr = _feat_array(feats)
+    _lib_call("shard_fill", arr, len(feats), batch, world, ptr(counts), ptr(slot), ptr(keys), ptr(pos), stream())
+    return keys, pos
+
+
+def _ptr_array(tensors):
+    return (C.c_void_p * len(tensors))(*[t.data_ptr() if t is not None else None for t in tensors])
+
+
+def shard_gather_rows(tables, lin_tables, dim, keys, n):
+    dev = keys.device
+    rows = torch.empty((max(n, 1), dim), dtype=torch.float32, device=dev)
+    lin = torch.empty((max(n, 1),), dtype=torch.float32, device=dev) if lin_tables is not None else None
+    _lib_call("shard_gather_rows", _ptr_array(tables), _ptr_array(lin_tables) if lin_tables is not None else None,
+              len(tables), dim, ptr(keys), n, ptr(rows), ptr(lin), stream())
+    return rows, lin
+
+
+def shard_scatter_rows(tables, lin_tables, dim, keys, n, grows, glin, scale, lin_scale):
+    _lib_call("shard_scatter_rows", _ptr_array(tables), _ptr_array(lin_tables) if lin_tables is not None else None,
+              len(tables), dim, ptr(keys), n, ptr(grows), ptr(glin), scale, lin_scale, stream())
+
+
+for _n in ("shard_bucketize", "shard_fill", "shard_gather_rows", "shard_scatter_rows"):
+    globals()[_n] = _timed(globals()[_n])

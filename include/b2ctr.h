@@ -361,6 +361,29 @@ B2CTR_API b2ctr_status_t b2ctr_dice_bwd(const float* x, const float* mean, const
 B2CTR_API b2ctr_status_t b2ctr_dropout(const float* x, float* y, int64_t n, float rate, uint64_t seed,
                                       void* stream);
 
+/* ------------------------------------------------------------------------------------------ */
+/* 7. Row-sharded embedding exchange (new capability, no reference counterpart)     */
+/*    row r of every table lives on rank r % world as local row r / world.                        */
+/* ------------------------------------------------------------------------------------------ */
+/* pass 1: counts[owner] += #lookups owned by `owner` (counts must be zero on entry);
+ * slot[b*nfeat+f] = owner << 32 | rank-inside-the-owner's-bucket.  feats[f].{idx,idx_stride,idx_dtype}. */
+B2CTR_API b2ctr_status_t b2ctr_shard_bucketize(const b2ctr_feature_t* feats, int32_t nfeat, int64_t batch,
+                                              int32_t world, int32_t* counts, int64_t* slot, void* stream);
+/* pass 2: keys grouped by owner (key = feature << 40 | local_row) and pos[b*nfeat+f] = index of that
+ * lookup inside keys (= row of the answer in the buffer the owners send back).                    */
+B2CTR_API b2ctr_status_t b2ctr_shard_fill(const b2ctr_feature_t* feats, int32_t nfeat, int64_t batch,
+                                         int32_t world, const int32_t* counts, const int64_t* slot,
+                                         int64_t* keys, int32_t* pos, void* stream);
+/* owner: rows[i,:] = tables[f][row,:], lin_out[i] = lin_tables[f][row] for keys[i] = f << 40 | row */
+B2CTR_API b2ctr_status_t b2ctr_shard_gather_rows(float* const* tables, float* const* lin_tables,
+                                                int32_t nfeat, int32_t dim, const int64_t* keys, int64_t n,
+                                                float* rows, float* lin_out, void* stream);
+/* owner, backward: tables[f][row,:] += scale * grows[i,:]; lin_tables[f][row] += lin_scale * glin[i] */
+B2CTR_API b2ctr_status_t b2ctr_shard_scatter_rows(float* const* tables, float* const* lin_tables,
+                                                 int32_t nfeat, int32_t dim, const int64_t* keys, int64_t n,
+                                                 const float* grows, const float* glin, float scale,
+                                                 float lin_scale, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -10,6 +10,7 @@
 //   * every lane keeps up to 8 independent 16 B loads in flight (Little's law at 6.5 TB/s);
 //   * row updates are REDG.E.ADD.F32x4 (the add executes in the L2 slice, no read by the SM);
 //   * grids are whole multiples of 148 SMs.
+#include <stdlib.h>
 #include "common.cuh"
 
 namespace b2ctr {
@@ -392,6 +393,7 @@ struct UniParams {
   int32_t dim;
   int32_t idx_dtype;
   int32_t has_lin;
+  int32_t l2_hints;
 };
 
 __device__ __forceinline__ int64_t uni_id(const UniParams& p, int f, int64_t b) {
@@ -410,6 +412,8 @@ __global__ void __launch_bounds__(256, 4)
   const int lane = threadIdx.x & 31;
   const int slot = lane / LPR, chunk = lane % LPR;
   const int F = p.nfeat, dim = p.dim;
+  const bool hints = p.l2_hints != 0;
+  const uint64_t pol_keep = l2_policy_evict_last(), pol_stream = l2_policy_evict_first();
   const int64_t nwarps = (int64_t)gridDim.x * (blockDim.x >> 5);
   int64_t b = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   // ids: lane l holds features l and l+32
@@ -431,13 +435,17 @@ __global__ void __launch_bounds__(256, 4)
         const int64_t ida = __shfl_sync(0xffffffffu, id0, fs & 31);
         const int64_t idb = __shfl_sync(0xffffffffu, id1, fs & 31);
         const int64_t id = fs < 32 ? ida : idb;
-        if (f < F) v[u] = ldg_stream_f4(p.table[f] + id * dim + chunk * 4);
+        if (f < F) {
+          const float* src = p.table[f] + id * dim + chunk * 4;
+          v[u] = hints ? ldg_stream_f4_pol(src, pol_stream) : ldg_stream_f4(src);
+        }
       }
 #pragma unroll
       for (int u = 0; u < U; ++u) {
         const int f = f0 + u * RPI + slot;
         if (f < F) {
-          stg_stream_f4(xrow + (int64_t)f * dim + chunk * 4, v[u]);
+          if (hints) stg_stream_f4_pol(xrow + (int64_t)f * dim + chunk * 4, v[u], pol_stream);
+          else stg_stream_f4(xrow + (int64_t)f * dim + chunk * 4, v[u]);
           if ((p.fm_mask >> f) & 1ull) {
             s.x += v[u].x; s.y += v[u].y; s.z += v[u].z; s.w += v[u].w;
             q += v[u].x * v[u].x + v[u].y * v[u].y + v[u].z * v[u].z + v[u].w * v[u].w;
@@ -462,8 +470,8 @@ __global__ void __launch_bounds__(256, 4)
     if (p.linear != nullptr) {
       float l = 0.f;
       if (p.has_lin) {
-        if (lane < F) l += p.lin[lane][id0];
-        if (lane + 32 < F) l += p.lin[lane + 32][id1];
+        if (lane < F) l += hints ? ldg_f1_pol(p.lin[lane] + id0, pol_keep) : p.lin[lane][id0];
+        if (lane + 32 < F) l += hints ? ldg_f1_pol(p.lin[lane + 32] + id1, pol_keep) : p.lin[lane + 32][id1];
       }
       l = warp_sum(l);
       if (lane == 0) p.linear[b] = l;
@@ -491,6 +499,8 @@ __global__ void __launch_bounds__(256, 3)
   const int lane = threadIdx.x & 31;
   const int slot = lane / LPR, chunk = lane % LPR;
   const int F = p.nfeat, dim = p.dim;
+  const bool hints = p.l2_hints != 0;
+  const uint64_t pol_keep = l2_policy_evict_last(), pol_stream = l2_policy_evict_first();
   const int64_t nwarps = (int64_t)gridDim.x * (blockDim.x >> 5);
   int64_t b = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   int64_t id0 = (b < batch && lane < F) ? uni_id(p, lane, b) : 0;
@@ -533,7 +543,7 @@ __global__ void __launch_bounds__(256, 3)
         xv[u] = g[u];
         if (f < F) {
           const int64_t off = (int64_t)f * dim + chunk * 4;
-          if (dxrow) g[u] = ldg_stream_f4(dxrow + off);
+          if (dxrow) g[u] = hints ? ldg_stream_f4_pol(dxrow + off, pol_stream) : ldg_stream_f4(dxrow + off);
           if (dfm && ((p.fm_mask >> f) & 1ull)) xv[u] = *reinterpret_cast<const float4*>(xrow + off);  // L1 hit
         }
       }
@@ -553,14 +563,15 @@ __global__ void __launch_bounds__(256, 3)
             r.w += gfm * (s.w - xv[u].w);
           }
           r.x *= scale; r.y *= scale; r.z *= scale; r.w *= scale;
-          red_add_f4(p.table[f] + id * dim + chunk * 4, r);
+          if (hints) red_add_f4_pol(p.table[f] + id * dim + chunk * 4, r, pol_stream);
+          else red_add_f4(p.table[f] + id * dim + chunk * 4, r);
         }
       }
     }
     if (dlinear && p.has_lin) {
       const float gl = dlinear[b] * lin_scale;
-      if (lane < F) red_add_f1(p.lin[lane] + id0, gl);
-      if (lane + 32 < F) red_add_f1(p.lin[lane + 32] + id1, gl);
+      if (lane < F) { if (hints) red_add_f1_pol(p.lin[lane] + id0, gl, pol_keep); else red_add_f1(p.lin[lane] + id0, gl); }
+      if (lane + 32 < F) { if (hints) red_add_f1_pol(p.lin[lane + 32] + id1, gl, pol_keep); else red_add_f1(p.lin[lane + 32] + id1, gl); }
     }
     id0 = nid0;
     id1 = nid1;
@@ -709,6 +720,9 @@ static b2ctr_status_t fill_uni(const b2ctr_uniform_gather_t* g, UniParams* p) {
   p->dim = dim;
   p->idx_dtype = g->feats[0].idx_dtype;
   p->has_lin = g->lin_tables != nullptr;
+  static int hints = -1;
+  if (hints < 0) { const char* ev = getenv("B2CTR_L2_HINTS"); hints = ev ? atoi(ev) : 1; }
+  p->l2_hints = hints;
   return B2CTR_OK;
 }
 

@@ -56,7 +56,7 @@ class Gemm(C.Structure):
                 ("lda", C.c_int64), ("ldb", C.c_int64), ("ldc", C.c_int64),
                 ("trans_a", C.c_int32), ("trans_b", C.c_int32), ("act", C.c_int32),
                 ("accumulate", C.c_int32), ("precision", C.c_int32), ("split_k", C.c_int32),
-                ("alpha", C.c_float), ("reserved", C.c_int32)]
+                ("alpha", C.c_float), ("variant", C.c_int32)]
 
 
 _vp, _i32, _i64, _f32, _sz, _u64 = C.c_void_p, C.c_int32, C.c_int64, C.c_float, C.c_size_t, C.c_uint64

@@ -338,12 +338,362 @@ static cudaError_t launch_tc(const TcArgs& ta, bool akc, bool bkc, cudaStream_t 
   return cudaGetLastError();
 }
 
+// ================================================================================================
+// Variant 2 ("planes"): the fp32 -> (hi, lo) bf16 split is done ONCE per operand by a streaming kernel
+// into K-major planes [rows_pad, k_pad] in workspace memory; the GEMM kernel then only moves bytes:
+// 8 warps cp.async 16-byte chunks of the planes into the swizzled UMMA tiles (3-stage pipeline, no
+// register staging, no conversion instructions), 1 warp issues the same 3 UMMAs per K-step.
+// ncu on variant 1 (profiles/r1_gemm_tc_3stage.txt: tensor pipe ~7 %, warps active 14 %) showed the
+// producers, not the tensor core, bound the kernel: every CTA re-converted both operand tiles.
+// ================================================================================================
+struct PlaneArgs {
+  const __nv_bfloat16* a_hi; const __nv_bfloat16* a_lo;   // [m_pad, k_pad]
+  const __nv_bfloat16* b_hi; const __nv_bfloat16* b_lo;   // [n_pad, k_pad]
+  float* c; const float* bias; float* ws;
+  int64_t m, n, k_pad;
+  int64_t ldc;
+  int64_t k_per_split;
+  float alpha;
+  int act, accumulate, splits;
+};
+
+// dst planes [rows_pad, k_pad] <- src(r, k) = p[r*sr + k*sk]; zero outside [rows, k).
+// K-contiguous source: thread = (row, 8 consecutive k).
+__global__ void __launch_bounds__(256)
+    split_planes_kernel(const float* __restrict__ p, int64_t sr, int64_t rows, int64_t k, int64_t rows_pad,
+                        int64_t k_pad, __nv_bfloat16* hi, __nv_bfloat16* lo, int vec_ok) {
+  const int64_t chunks = k_pad / 8;
+  const int64_t total = rows_pad * chunks;
+  for (int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; t < total;
+       t += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t r = t / chunks;
+    const int64_t k0 = (t - r * chunks) * 8;
+    float v[8];
+    if (r < rows && vec_ok && k0 + 8 <= k) {
+      const float4 a = __ldg(reinterpret_cast<const float4*>(p + r * sr + k0));
+      const float4 b = __ldg(reinterpret_cast<const float4*>(p + r * sr + k0) + 1);
+      v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w; v[4] = b.x; v[5] = b.y; v[6] = b.z; v[7] = b.w;
+    } else {
+#pragma unroll
+      for (int j = 0; j < 8; ++j) v[j] = (r < rows && k0 + j < k) ? __ldg(p + r * sr + k0 + j) : 0.f;
+    }
+    uint32_t h[4], l[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const __nv_bfloat16 h0 = __float2bfloat16_rn(v[2 * j]), h1 = __float2bfloat16_rn(v[2 * j + 1]);
+      h[j] = pack_bf16(h0, h1);
+      l[j] = pack_bf16(__float2bfloat16_rn(v[2 * j] - __bfloat162float(h0)),
+                       __float2bfloat16_rn(v[2 * j + 1] - __bfloat162float(h1)));
+    }
+    *reinterpret_cast<uint4*>(hi + r * k_pad + k0) = make_uint4(h[0], h[1], h[2], h[3]);
+    *reinterpret_cast<uint4*>(lo + r * k_pad + k0) = make_uint4(l[0], l[1], l[2], l[3]);
+  }
+}
+// Row-contiguous source (src(r,k) = p[k*sk + r]): 64 x 64 tile transposed through shared memory.
+__global__ void __launch_bounds__(256)
+    split_planes_t_kernel(const float* __restrict__ p, int64_t sk, int64_t rows, int64_t k, int64_t rows_pad,
+                          int64_t k_pad, __nv_bfloat16* hi, __nv_bfloat16* lo) {
+  __shared__ float tile[64][65];
+  const int64_t r0 = (int64_t)blockIdx.x * 64, k0 = (int64_t)blockIdx.y * 64;
+  const int tx = threadIdx.x & 63, ty = threadIdx.x >> 6;   // 64 x 4
+#pragma unroll 4
+  for (int kk = ty; kk < 64; kk += 4) {
+    const int64_t gr = r0 + tx, gk = k0 + kk;
+    tile[kk][tx] = (gr < rows && gk < k) ? __ldg(p + gk * sk + gr) : 0.f;
+  }
+  __syncthreads();
+  for (int t = threadIdx.x; t < 64 * 8; t += 256) {
+    const int r = t >> 3, c = t & 7;
+    const int64_t gr = r0 + r;
+    if (gr >= rows_pad) continue;
+    uint32_t h[4], l[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const float v0 = tile[c * 8 + 2 * j][r], v1 = tile[c * 8 + 2 * j + 1][r];
+      const __nv_bfloat16 h0 = __float2bfloat16_rn(v0), h1 = __float2bfloat16_rn(v1);
+      h[j] = pack_bf16(h0, h1);
+      l[j] = pack_bf16(__float2bfloat16_rn(v0 - __bfloat162float(h0)), __float2bfloat16_rn(v1 - __bfloat162float(h1)));
+    }
+    *reinterpret_cast<uint4*>(hi + gr * k_pad + k0 + c * 8) = make_uint4(h[0], h[1], h[2], h[3]);
+    *reinterpret_cast<uint4*>(lo + gr * k_pad + k0 + c * 8) = make_uint4(l[0], l[1], l[2], l[3]);
+  }
+}
+
+__device__ __forceinline__ void cp_async16(uint32_t dst, const void* src) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(src) : "memory");
+}
+
+template <int BN, int STAGES>
+__global__ void __launch_bounds__(kTcThreads, 1) gemm_planes_kernel(const PlaneArgs g) {
+  constexpr int A_PLANE = kTM * 128;
+  constexpr int B_PLANE = BN * 128;
+  constexpr int STAGE = 2 * A_PLANE + 2 * B_PLANE;
+  extern __shared__ unsigned char smem_raw[];
+  unsigned char* tiles = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) &
+                                                          ~(uintptr_t)1023);
+  __shared__ __align__(8) uint64_t full_bar[STAGES], empty_bar[STAGES], accum_bar;
+  __shared__ uint32_t tmem_slot;
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int64_t m0 = (int64_t)blockIdx.y * kTM, n0 = (int64_t)blockIdx.x * BN;
+  const int64_t kbeg = (int64_t)blockIdx.z * g.k_per_split;
+  const int64_t kend = kbeg + g.k_per_split < g.k_pad ? kbeg + g.k_per_split : g.k_pad;
+  const int nkb = kend > kbeg ? (int)((kend - kbeg) / kTK) : 0;
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < STAGES; ++s) {
+      mbar_init(&full_bar[s], kProducerWarps);
+      mbar_init(&empty_bar[s], 1);
+    }
+    mbar_init(&accum_bar, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == kProducerWarps) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(
+                     smem_u32(&tmem_slot)),
+                 "r"((uint32_t)(BN < 32 ? 32 : BN))
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+  const uint32_t tmem_base = tmem_slot;
+
+  if (warp < kProducerWarps) {
+    const int tid = threadIdx.x;
+    // software pipeline over k-blocks: issue the copies of block `kb`, then publish block kb-(STAGES-1)
+    for (int kb = 0; kb < nkb + STAGES - 1; ++kb) {
+      if (kb < nkb) {
+        const int s = kb % STAGES;
+        mbar_wait(&empty_bar[s], ((kb / STAGES) & 1) ^ 1);
+        const uint32_t st = smem_u32(tiles + (size_t)s * STAGE);
+        const int64_t k0 = kbeg + (int64_t)kb * kTK;
+#pragma unroll
+        for (int t = tid; t < kTM * 8; t += kProducerWarps * 32) {
+          const int r = t >> 3, c = t & 7;
+          const uint32_t off = r * 128 + ((c ^ (r & 7)) << 4);
+          const int64_t src = (m0 + r) * g.k_pad + k0 + c * 8;
+          cp_async16(st + off, g.a_hi + src);
+          cp_async16(st + A_PLANE + off, g.a_lo + src);
+        }
+#pragma unroll
+        for (int t = tid; t < BN * 8; t += kProducerWarps * 32) {
+          const int r = t >> 3, c = t & 7;
+          const uint32_t off = r * 128 + ((c ^ (r & 7)) << 4);
+          const int64_t src = (n0 + r) * g.k_pad + k0 + c * 8;
+          cp_async16(st + 2 * A_PLANE + off, g.b_hi + src);
+          cp_async16(st + 2 * A_PLANE + B_PLANE + off, g.b_lo + src);
+        }
+      }
+      asm volatile("cp.async.commit_group;" ::: "memory");
+      if (kb >= STAGES - 1) {
+        const int j = kb - (STAGES - 1);
+        asm volatile("cp.async.wait_group %0;" ::"n"(STAGES - 1) : "memory");
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&full_bar[j % STAGES]);
+      }
+    }
+    // ---- epilogue (same as variant 1) ----
+    if (nkb > 0) {
+      mbar_wait(&accum_bar, 0);
+      asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    }
+    const int sub = warp & 3;
+    const int half = warp >> 2;
+    constexpr int HALVES = BN >= 64 ? 2 : 1;
+    constexpr int COLS = BN / HALVES;
+    const int64_t gm = m0 + sub * 32 + lane;
+    const bool vec_c = (g.ldc % 4 == 0) && ((reinterpret_cast<uintptr_t>(g.c) & 15) == 0) &&
+                       (!g.bias || (reinterpret_cast<uintptr_t>(g.bias) & 15) == 0) && g.splits == 1;
+    if (half < HALVES) {
+#pragma unroll 1
+      for (int c0 = 0; c0 < COLS; c0 += 32) {
+        uint32_t r[32];
+        if (nkb > 0) {
+          const uint32_t taddr = tmem_base + ((uint32_t)(sub * 32) << 16) + (uint32_t)(half * COLS + c0);
+          asm volatile(
+              "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+              "{%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,"
+              "%16,%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,%29,%30,%31}, [%32];\n"
+              : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]),
+                "=r"(r[7]), "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]),
+                "=r"(r[14]), "=r"(r[15]), "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]),
+                "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]),
+                "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+              : "r"(taddr));
+          asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+        } else {
+#pragma unroll
+          for (int j = 0; j < 32; ++j) r[j] = 0u;
+        }
+        if (gm < g.m) {
+          const int64_t gn0 = n0 + half * COLS + c0;
+          if (vec_c && gn0 + 32 <= g.n) {
+            float* crow = g.c + gm * g.ldc + gn0;
+#pragma unroll
+            for (int j = 0; j < 32; j += 4) {
+              float4 v = make_float4(g.alpha * __uint_as_float(r[j]), g.alpha * __uint_as_float(r[j + 1]),
+                                     g.alpha * __uint_as_float(r[j + 2]), g.alpha * __uint_as_float(r[j + 3]));
+              if (g.accumulate) {
+                const float4 o = *reinterpret_cast<const float4*>(crow + j);
+                v.x += o.x; v.y += o.y; v.z += o.z; v.w += o.w;
+              }
+              if (g.bias) {
+                const float4 bb = __ldg(reinterpret_cast<const float4*>(g.bias + gn0 + j));
+                v.x += bb.x; v.y += bb.y; v.z += bb.z; v.w += bb.w;
+              }
+              v.x = act_apply(v.x, g.act); v.y = act_apply(v.y, g.act);
+              v.z = act_apply(v.z, g.act); v.w = act_apply(v.w, g.act);
+              *reinterpret_cast<float4*>(crow + j) = v;
+            }
+          } else {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) {
+              const int64_t gn = gn0 + j;
+              if (gn < g.n) {
+                float v = g.alpha * __uint_as_float(r[j]);
+                if (g.splits > 1) {
+                  g.ws[((int64_t)blockIdx.z * g.m + gm) * g.n + gn] = v;
+                } else {
+                  if (g.accumulate) v += g.c[gm * g.ldc + gn];
+                  if (g.bias) v += g.bias[gn];
+                  g.c[gm * g.ldc + gn] = act_apply(v, g.act);
+                }
+              }
+            }
+          }
+        }
+      }
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  } else {
+    const uint32_t idesc = umma_idesc(BN);
+    for (int kb = 0; kb < nkb; ++kb) {
+      const int s = kb % STAGES;
+      mbar_wait(&full_bar[s], (kb / STAGES) & 1);
+      asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+      if (lane == 0) {
+        const uint32_t sa = smem_u32(tiles + (size_t)s * STAGE);
+        const uint32_t a_hi = sa, a_lo = sa + A_PLANE, b_hi = sa + 2 * A_PLANE, b_lo = sa + 2 * A_PLANE + B_PLANE;
+#pragma unroll
+        for (int ks = 0; ks < kTK / 16; ++ks) {
+          const uint32_t ko = ks * 32;
+          umma_f16(tmem_base, umma_desc(a_hi + ko), umma_desc(b_hi + ko), idesc, (kb | ks) ? 1u : 0u);
+          umma_f16(tmem_base, umma_desc(a_hi + ko), umma_desc(b_lo + ko), idesc, 1u);
+          umma_f16(tmem_base, umma_desc(a_lo + ko), umma_desc(b_hi + ko), idesc, 1u);
+        }
+        umma_commit(&empty_bar[s]);
+        if (kb == nkb - 1) umma_commit(&accum_bar);
+      }
+      __syncwarp();
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  }
+  __syncthreads();
+  if (warp == kProducerWarps) {
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base),
+                 "r"((uint32_t)(BN < 32 ? 32 : BN))
+                 : "memory");
+  }
+}
+
+template <int BN, int STAGES>
+static cudaError_t launch_planes(const PlaneArgs& pa, cudaStream_t st) {
+  constexpr size_t smem = (size_t)STAGES * (2 * kTM * 128 + 2 * BN * 128) + 1024;
+  dim3 grid((unsigned)ceil_div(pa.n, BN), (unsigned)ceil_div(pa.m, kTM), (unsigned)pa.splits);
+  auto kern = gemm_planes_kernel<BN, STAGES>;
+  cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  if (e != cudaSuccess) return e;
+  kern<<<grid, kTcThreads, smem, st>>>(pa);
+  return cudaGetLastError();
+}
+
+static inline int64_t round_up(int64_t v, int64_t q) { return (v + q - 1) / q * q; }
+static inline int planes_bn(int64_t n) { return n <= 32 ? 32 : (n <= 64 ? 64 : (n <= 128 ? 128 : 256)); }
+
+static int tc_variant(const b2ctr_gemm_t* g) {
+  if (g->variant == 1 || g->variant == 2) return g->variant;
+  static int mode = -1;
+  if (mode < 0) {
+    const char* ev = getenv("B2CTR_TC_VARIANT");
+    mode = ev ? atoi(ev) : 2;
+  }
+  return mode == 1 ? 1 : 2;
+}
+
 size_t gemm_bf16x3_workspace_bytes(const b2ctr_gemm_t* g) {
-  return g->split_k > 1 ? (size_t)g->split_k * g->m * g->n * sizeof(float) : 0;
+  size_t splitk = g->split_k > 1 ? (size_t)g->split_k * g->m * g->n * sizeof(float) : 0;
+  if (tc_variant(g) == 1) return splitk;
+  const int bn = planes_bn(g->n);
+  const int64_t kp = round_up(g->k > 0 ? g->k : 1, kTK), mp = round_up(g->m, kTM), np = round_up(g->n, bn);
+  return splitk + (size_t)(mp + np) * kp * 2 * sizeof(__nv_bfloat16) + 512;
+}
+
+static b2ctr_status_t gemm_planes(const b2ctr_gemm_t* g, void* workspace, size_t workspace_bytes, cudaStream_t st) {
+  const size_t need = gemm_bf16x3_workspace_bytes(g);
+  if (!workspace || workspace_bytes < need) {
+    set_error("gemm(bf16x3): needs %zu workspace bytes, got %zu", need, workspace_bytes);
+    return B2CTR_ERR_WORKSPACE;
+  }
+  const int splits = g->split_k > 1 ? g->split_k : 1;
+  const int bn = planes_bn(g->n);
+  const int64_t kp = round_up(g->k > 0 ? g->k : 1, kTK), mp = round_up(g->m, kTM), np = round_up(g->n, bn);
+  unsigned char* w = (unsigned char*)workspace;
+  float* ws = (float*)w;
+  w += splits > 1 ? (size_t)splits * g->m * g->n * sizeof(float) : 0;
+  w = (unsigned char*)(((uintptr_t)w + 255) & ~(uintptr_t)255);
+  __nv_bfloat16* a_hi = (__nv_bfloat16*)w;
+  __nv_bfloat16* a_lo = a_hi + mp * kp;
+  __nv_bfloat16* b_hi = a_lo + mp * kp;
+  __nv_bfloat16* b_lo = b_hi + np * kp;
+  // operand splits (one streaming pass each)
+  auto split = [&](const float* p, bool k_contig, int64_t ld, int64_t rows, int64_t rows_pad,
+                   __nv_bfloat16* hi, __nv_bfloat16* lo) {
+    if (k_contig) {
+      const int vec = (ld % 4 == 0) && (((uintptr_t)p & 15) == 0);
+      split_planes_kernel<<<grid_for(rows_pad * (kp / 8), 256, 8), 256, 0, st>>>(p, ld, rows, g->k, rows_pad, kp,
+                                                                               hi, lo, vec);
+    } else {
+      dim3 grid((unsigned)ceil_div(rows_pad, 64), (unsigned)(kp / 64));
+      split_planes_t_kernel<<<grid, 256, 0, st>>>(p, ld, rows, g->k, rows_pad, kp, hi, lo);
+    }
+  };
+  split(g->a, !g->trans_a, g->lda, g->m, mp, a_hi, a_lo);
+  B2_CHECK_LAUNCH("b2ctr_gemm(bf16x3 split A)");
+  split(g->b, g->trans_b != 0, g->ldb, g->n, np, b_hi, b_lo);
+  B2_CHECK_LAUNCH("b2ctr_gemm(bf16x3 split B)");
+  PlaneArgs pa;
+  pa.a_hi = a_hi; pa.a_lo = a_lo; pa.b_hi = b_hi; pa.b_lo = b_lo;
+  pa.c = g->c; pa.bias = g->bias; pa.ws = ws;
+  pa.m = g->m; pa.n = g->n; pa.k_pad = kp; pa.ldc = g->ldc;
+  pa.k_per_split = ceil_div(ceil_div(kp, splits), kTK) * kTK;
+  pa.alpha = g->alpha; pa.act = g->act; pa.accumulate = g->accumulate; pa.splits = splits;
+  cudaError_t e;
+  if (bn == 32) e = launch_planes<32, 4>(pa, st);
+  else if (bn == 64) e = launch_planes<64, 4>(pa, st);
+  else if (bn == 128) e = launch_planes<128, 3>(pa, st);
+  else e = launch_planes<256, 2>(pa, st);
+  if (e != cudaSuccess) {
+    set_error("b2ctr_gemm(bf16x3 planes): CUDA launch failed: %s", cudaGetErrorString(e));
+    return B2CTR_ERR_CUDA;
+  }
+  count_launch();
+  if (splits > 1) {
+    TcArgs ta;
+    ta.c = g->c; ta.bias = g->bias; ta.ws = ws; ta.m = g->m; ta.n = g->n; ta.ldc = g->ldc;
+    ta.act = g->act; ta.accumulate = g->accumulate; ta.splits = splits;
+    tc_splitk_reduce_kernel<<<grid_for(g->m * g->n, 256, 4), 256, 0, st>>>(ta);
+    B2_CHECK_LAUNCH("b2ctr_gemm(bf16x3 splitk_reduce)");
+  }
+  return B2CTR_OK;
 }
 
 b2ctr_status_t gemm_bf16x3(const b2ctr_gemm_t* g, void* workspace, size_t workspace_bytes,
                            cudaStream_t st) {
+  if (tc_variant(g) == 2) return gemm_planes(g, workspace, workspace_bytes, st);
   TcArgs ta;
   ta.a = g->a; ta.b = g->b; ta.c = g->c; ta.bias = g->bias; ta.ws = (float*)workspace;
   ta.m = g->m; ta.n = g->n; ta.k = g->k;
@@ -362,19 +712,16 @@ b2ctr_status_t gemm_bf16x3(const b2ctr_gemm_t* g, void* workspace, size_t worksp
   const bool akc = !g->trans_a;   // A stored [M,K]: K contiguous
   const bool bkc = g->trans_b != 0;  // B stored [N,K]: K contiguous
   cudaError_t e;
-  // Two pipeline shapes: (a) deep intra-CTA pipeline, 1 CTA per SM; (b) single stage, 3 CTAs per SM, so the
-  // global-load latency of one CTA's producers overlaps the convert / MMA phases of its neighbours.
-  // (b) wins for these producer-bound shapes (profiles/r1_gemm_tc.txt); B2CTR_TC_STAGES overrides.
   static int stages_mode = -1;
   if (stages_mode < 0) {
     const char* ev = getenv("B2CTR_TC_STAGES");
     stages_mode = ev ? atoi(ev) : 1;
   }
-  if (stages_mode == 1) {
+  if (stages_mode == 1) {        // single stage, 3 CTAs per SM: neighbours hide each other's load latency
     if (g->n <= 32) e = launch_tc<32, 1>(ta, akc, bkc, st);
     else if (g->n <= 64) e = launch_tc<64, 1>(ta, akc, bkc, st);
     else e = launch_tc<128, 1>(ta, akc, bkc, st);
-  } else {
+  } else {                       // deep intra-CTA pipeline, 1 CTA per SM
     if (g->n <= 32) e = launch_tc<32, 4>(ta, akc, bkc, st);
     else if (g->n <= 64) e = launch_tc<64, 4>(ta, akc, bkc, st);
     else e = launch_tc<128, 3>(ta, akc, bkc, st);

@@ -143,7 +143,7 @@ def init_normal(dst, mean, std, seed):
 
 # ---- GEMM -----------------------------------------------------------------------------------
 def gemm(a, b, c=None, bias=None, trans_a=False, trans_b=False, act=L.ACT_NONE, accumulate=False,
-         precision=L.GEMM_FP32, split_k=1, alpha=1.0, m=None, n=None, k=None):
+         precision=L.GEMM_FP32, split_k=1, alpha=1.0, m=None, n=None, k=None, variant=0):
     """C[M,N] = act(alpha * op(A) @ op(B) + bias) on 2-D row-major (possibly ld-padded) tensors."""
     _require_cuda(a, b, c, bias)
     if m is None:
@@ -161,6 +161,7 @@ def gemm(a, b, c=None, bias=None, trans_a=False, trans_b=False, act=L.ACT_NONE, 
     g.lda, g.ldb, g.ldc = a.stride(0), b.stride(0), c.stride(0)
     g.trans_a, g.trans_b = int(trans_a), int(trans_b)
     g.act, g.accumulate, g.precision, g.split_k, g.alpha = act, int(accumulate), precision, split_k, alpha
+    g.variant = variant
     nbytes = L.lib().b2ctr_gemm_workspace_bytes(C.byref(g))
     ws = workspace(nbytes, a.device)
     L.check(L.lib().b2ctr_gemm(C.byref(g), ptr(ws), nbytes if ws is not None else 0, stream()), "gemm")

@@ -176,7 +176,7 @@ typedef struct b2ctr_gemm {
   int32_t precision;       /* B2CTR_GEMM_*                                                     */
   int32_t split_k;         /* >1: split the K loop over this many CTAs (needs workspace)       */
   float alpha;             /* scales op(A)@op(B)                                               */
-  int32_t reserved;
+  int32_t variant;         /* BF16X3 only: 0 default, 1 in-kernel split, 2 pre-split planes (testing)  */
 } b2ctr_gemm_t;
 
 B2CTR_API size_t b2ctr_gemm_workspace_bytes(const b2ctr_gemm_t* g);

@@ -180,7 +180,8 @@ def test_optimizers(cuda):
 @pytest.mark.parametrize("m,n,k", [(128, 128, 64), (1, 1, 1), (257, 256, 845), (130, 64, 128), (1000, 1, 64),
                                    (64, 300, 7), (4096, 256, 848), (300, 40, 200)])
 @pytest.mark.parametrize("ta,tb", [(False, False), (False, True), (True, False), (True, True)])
-def test_gemm_bf16x3_tensor_core(cuda, m, n, k, ta, tb):
+@pytest.mark.parametrize("variant", [1, 2])      # 1: split inside the GEMM producers, 2: pre-split planes
+def test_gemm_bf16x3_tensor_core(cuda, m, n, k, ta, tb, variant):
     """tcgen05 split-bf16 GEMM: error bound ~2^-16 relative to sum |a||b|."""
     K, L = _kern()
     rng = np.random.RandomState(m + 3 * n + k)
@@ -191,12 +192,13 @@ def test_gemm_bf16x3_tensor_core(cuda, m, n, k, ta, tb):
     Bm = (b.t() if tb else b).double()
     want = torch.relu(A @ Bm + bias.double())
     got = K.gemm(a.to(cuda), b.to(cuda), bias=bias.to(cuda), trans_a=ta, trans_b=tb, act=L.ACT_RELU,
-                 precision=L.GEMM_BF16X3, m=m, n=n, k=k).cpu().double()
+                 precision=L.GEMM_BF16X3, m=m, n=n, k=k, variant=variant).cpu().double()
     bound = (A.abs() @ Bm.abs()) * 2.0 ** -15 + 1e-6
     assert ((got - want).abs() <= bound).all(), float(((got - want).abs() / bound).max())
 
 
-def test_gemm_bf16x3_splitk_accumulate(cuda):
+@pytest.mark.parametrize("variant", [1, 2])
+def test_gemm_bf16x3_splitk_accumulate(cuda, variant):
     K, L = _kern()
     rng = np.random.RandomState(77)
     m, n, k = 845, 256, 8200
@@ -206,7 +208,7 @@ def test_gemm_bf16x3_splitk_accumulate(cuda):
     want = c0.double() + 0.5 * (xd.cpu()[:, :m].t().double() @ dy.cpu().double())
     c = c0.to(cuda)
     K.gemm(xd, dy, c=c, trans_a=True, accumulate=True, split_k=8, alpha=0.5, precision=L.GEMM_BF16X3,
-           m=m, n=n, k=k)
+           m=m, n=n, k=k, variant=variant)
     bound = (xd.cpu()[:, :m].t().double().abs() @ dy.cpu().double().abs()) * 2.0 ** -15 + 1e-5
     assert ((c.cpu().double() - want).abs() <= bound).all()
     # against the exact-fp32 path on the same inputs

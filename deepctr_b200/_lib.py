@@ -23,6 +23,7 @@ ACT_NONE, ACT_RELU, ACT_SIGMOID, ACT_TANH = 0, 1, 2, 3
 GEMM_FP32, GEMM_BF16X3 = 0, 1
 TASK_BINARY, TASK_REGRESSION = 0, 1
 MAX_FEATURES = 128
+UNIFORM_STORE_GRADS = 1
 
 ACT_BY_NAME = {None: ACT_NONE, "linear": ACT_NONE, "relu": ACT_RELU, "sigmoid": ACT_SIGMOID,
                "tanh": ACT_TANH}
@@ -46,7 +47,7 @@ class UniformGather(C.Structure):
                 ("dense", C.c_void_p), ("x", C.c_void_p), ("linear", C.c_void_p), ("fm", C.c_void_p),
                 ("ldx", C.c_int64), ("dense_ld", C.c_int64), ("x_cols", C.c_int64),
                 ("nfeat", C.c_int32),
-                ("ndense", C.c_int32), ("fm_mask", C.c_uint64 * 2)]
+                ("ndense", C.c_int32), ("fm_mask", C.c_uint64 * 2), ("flags", C.c_int32), ("reserved", C.c_int32)]
 
 
 class Gemm(C.Structure):

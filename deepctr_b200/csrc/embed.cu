@@ -394,6 +394,7 @@ struct UniParams {
   int32_t idx_dtype;
   int32_t has_lin;
   int32_t l2_hints;
+  int32_t store_grads;
 };
 
 __device__ __forceinline__ int64_t uni_id(const UniParams& p, int f, int64_t b) {
@@ -563,15 +564,21 @@ __global__ void __launch_bounds__(256, 3)
             r.w += gfm * (s.w - xv[u].w);
           }
           r.x *= scale; r.y *= scale; r.z *= scale; r.w *= scale;
-          if (hints) red_add_f4_pol(p.table[f] + id * dim + chunk * 4, r, pol_stream);
+          if (p.store_grads) stg_stream_f4(p.table[f] + id * dim + chunk * 4, r);
+          else if (hints) red_add_f4_pol(p.table[f] + id * dim + chunk * 4, r, pol_stream);
           else red_add_f4(p.table[f] + id * dim + chunk * 4, r);
         }
       }
     }
     if (dlinear && p.has_lin) {
       const float gl = dlinear[b] * lin_scale;
-      if (lane < F) { if (hints) red_add_f1_pol(p.lin[lane] + id0, gl, pol_keep); else red_add_f1(p.lin[lane] + id0, gl); }
-      if (lane + 32 < F) { if (hints) red_add_f1_pol(p.lin[lane + 32] + id1, gl, pol_keep); else red_add_f1(p.lin[lane + 32] + id1, gl); }
+      if (p.store_grads) {
+        if (lane < F) p.lin[lane][id0] = gl;
+        if (lane + 32 < F) p.lin[lane + 32][id1] = gl;
+      } else {
+        if (lane < F) { if (hints) red_add_f1_pol(p.lin[lane] + id0, gl, pol_keep); else red_add_f1(p.lin[lane] + id0, gl); }
+        if (lane + 32 < F) { if (hints) red_add_f1_pol(p.lin[lane + 32] + id1, gl, pol_keep); else red_add_f1(p.lin[lane + 32] + id1, gl); }
+      }
     }
     id0 = nid0;
     id1 = nid1;
@@ -723,6 +730,7 @@ static b2ctr_status_t fill_uni(const b2ctr_uniform_gather_t* g, UniParams* p) {
   static int hints = -1;
   if (hints < 0) { const char* ev = getenv("B2CTR_L2_HINTS"); hints = ev ? atoi(ev) : 1; }
   p->l2_hints = hints;
+  p->store_grads = (g->flags & B2CTR_UNIFORM_STORE_GRADS) ? 1 : 0;
   return B2CTR_OK;
 }
 

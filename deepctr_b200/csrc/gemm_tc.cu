@@ -423,8 +423,12 @@ __device__ __forceinline__ void cp_async16(uint32_t dst, const void* src) {
   asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(src) : "memory");
 }
 
+// CTAs per SM follow from the stage footprint: a single-stage 128x128 tile (65 KB) fits three times, so
+// short-K GEMMs (dgrad of the first layer: K = 256 = 4 k-blocks) overlap one CTA's epilogue with its
+// neighbours' main loops instead of idling the SM.
 template <int BN, int STAGES>
-__global__ void __launch_bounds__(kTcThreads, 1) gemm_planes_kernel(const PlaneArgs g) {
+__global__ void __launch_bounds__(kTcThreads, (STAGES * (2 * kTM * 128 + 2 * BN * 128) + 1024 <= 75 * 1024) ? 3 : 1)
+    gemm_planes_kernel(const PlaneArgs g) {
   constexpr int A_PLANE = kTM * 128;
   constexpr int B_PLANE = BN * 128;
   constexpr int STAGE = 2 * A_PLANE + 2 * B_PLANE;
@@ -612,7 +616,12 @@ static cudaError_t launch_planes(const PlaneArgs& pa, cudaStream_t st) {
 }
 
 static inline int64_t round_up(int64_t v, int64_t q) { return (v + q - 1) / q * q; }
-static inline int planes_bn(int64_t n) { return n <= 32 ? 32 : (n <= 64 ? 64 : (n <= 128 ? 128 : 256)); }
+static inline int planes_bn(int64_t n, int64_t k) {
+  if (n <= 32) return 32;
+  if (n <= 64) return 64;
+  if (n <= 128 || k <= 4 * kTK) return 128;   // short K: prefer 128-wide tiles, 3 CTAs per SM
+  return 256;
+}
 
 static int tc_variant(const b2ctr_gemm_t* g) {
   if (g->variant == 1 || g->variant == 2) return g->variant;
@@ -627,7 +636,7 @@ static int tc_variant(const b2ctr_gemm_t* g) {
 size_t gemm_bf16x3_workspace_bytes(const b2ctr_gemm_t* g) {
   size_t splitk = g->split_k > 1 ? (size_t)g->split_k * g->m * g->n * sizeof(float) : 0;
   if (tc_variant(g) == 1) return splitk;
-  const int bn = planes_bn(g->n);
+  const int bn = planes_bn(g->n, g->k / (g->split_k > 1 ? g->split_k : 1));
   const int64_t kp = round_up(g->k > 0 ? g->k : 1, kTK), mp = round_up(g->m, kTM), np = round_up(g->n, bn);
   return splitk + (size_t)(mp + np) * kp * 2 * sizeof(__nv_bfloat16) + 512;
 }
@@ -639,7 +648,7 @@ static b2ctr_status_t gemm_planes(const b2ctr_gemm_t* g, void* workspace, size_t
     return B2CTR_ERR_WORKSPACE;
   }
   const int splits = g->split_k > 1 ? g->split_k : 1;
-  const int bn = planes_bn(g->n);
+  const int bn = planes_bn(g->n, g->k / (g->split_k > 1 ? g->split_k : 1));
   const int64_t kp = round_up(g->k > 0 ? g->k : 1, kTK), mp = round_up(g->m, kTM), np = round_up(g->n, bn);
   unsigned char* w = (unsigned char*)workspace;
   float* ws = (float*)w;
@@ -672,9 +681,10 @@ static b2ctr_status_t gemm_planes(const b2ctr_gemm_t* g, void* workspace, size_t
   pa.k_per_split = ceil_div(ceil_div(kp, splits), kTK) * kTK;
   pa.alpha = g->alpha; pa.act = g->act; pa.accumulate = g->accumulate; pa.splits = splits;
   cudaError_t e;
-  if (bn == 32) e = launch_planes<32, 4>(pa, st);
-  else if (bn == 64) e = launch_planes<64, 4>(pa, st);
-  else if (bn == 128) e = launch_planes<128, 3>(pa, st);
+  const bool short_k = pa.k_per_split <= 4 * kTK;
+  if (bn == 32) e = short_k ? launch_planes<32, 1>(pa, st) : launch_planes<32, 4>(pa, st);
+  else if (bn == 64) e = short_k ? launch_planes<64, 1>(pa, st) : launch_planes<64, 4>(pa, st);
+  else if (bn == 128) e = short_k ? launch_planes<128, 1>(pa, st) : launch_planes<128, 3>(pa, st);
   else e = launch_planes<256, 2>(pa, st);
   if (e != cudaSuccess) {
     set_error("b2ctr_gemm(bf16x3 planes): CUDA launch failed: %s", cudaGetErrorString(e));

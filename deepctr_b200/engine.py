@@ -1093,15 +1093,24 @@ class Model(object):
             x, y, n = slice_inputs(x, slice(0, split)), y[:split], split
         rng = np.random.RandomState(kw.get("seed", None))
         for ep in range(epochs):
-            perm = rng.permutation(n) if shuffle else np.arange(n)
-            tot, cnt = 0.0, 0
-            sums = []
-            for s in range(0, n, batch_size):
-                idx = perm[s:s + batch_size]
+            perm = rng.permutation(n) if shuffle else None
+            cnt = 0
+            nsteps = (n + batch_size - 1) // batch_size
+            # every step's loss is read back (4 B, asynchronous D2H into pinned memory); the host only
+            # waits at the end of the epoch, so staging batch i+1 overlaps the kernels of batch i
+            host_losses = torch.empty((max(nsteps, 1),), dtype=torch.float32)
+            try:
+                host_losses = host_losses.pin_memory()
+            except Exception:
+                pass
+            for i, s in enumerate(range(0, n, batch_size)):
+                idx = perm[s:s + batch_size] if perm is not None else slice(s, min(n, s + batch_size))
                 ls, _, b = self._loss_step(slice_inputs(x, idx), y[idx], True)
-                sums.append(ls)
+                host_losses[i:i + 1].copy_(ls, non_blocking=True)
                 cnt += b
-            tot = float(torch.stack([t.reshape(()) for t in sums]).sum().item()) if sums else 0.0
+            torch.cuda.synchronize()
+            self.d2h_bytes = getattr(self, "d2h_bytes", 0) + 4 * nsteps
+            tot = float(host_losses[:nsteps].double().sum()) if nsteps else 0.0
             logs = {"loss": tot / max(cnt, 1) + self._reg_loss()}
             if val is not None:
                 logs["val_loss"] = self.evaluate(val[0], val[1], batch_size=batch_size)

@@ -600,11 +600,10 @@ class EmbeddingPlanner(object):
                 # and are applied there by the fused SGD scatter (scale = -lr / world: global-batch mean)
                 st, tabs, ltabs, dimf = self.route
                 dev = main.data.device
+                # every (b, f) owns a distinct row of the buffers: the scatter writes (no zero-fill, no RMW)
                 grows = torch.empty((st["n_send"], dimf), dtype=torch.float32, device=dev)
-                K.fill(grows, 0.0)
-                glin = None
-                if lin_fused:
-                    glin = torch.empty((st["n_send"],), dtype=torch.float32, device=dev)
+                glin = torch.empty((st["n_send"],), dtype=torch.float32, device=dev) if lin_fused else None
+                if dlin is None and glin is not None:
                     K.fill(glin, 0.0)
                 pos = st["pos"]
                 feats = [K.make_feature(grows, pos[:, f], main.data, out_col=s.col, out_ld=self.main_ld)
@@ -612,6 +611,7 @@ class EmbeddingPlanner(object):
                 bplan = K.UniformPlan(feats, [glin] * len(fast_slots) if lin_fused else None, None, main.data,
                                       None, None, plan.g.fm_mask[0])
                 bplan.g.x_cols = plan.g.x_cols
+                bplan.g.flags = L.UNIFORM_STORE_GRADS
                 K.embed_scatter_uniform_bwd(bplan, dx, None if dfm is None else dfm.reshape(-1).contiguous(),
                                             None if dlin is None else dlin.reshape(-1).contiguous(),
                                             1.0, 1.0, batch)

@@ -128,7 +128,12 @@ typedef struct b2ctr_uniform_gather {
   int32_t nfeat;
   int32_t ndense;
   uint64_t fm_mask[2];
+  int32_t flags;                /* B2CTR_UNIFORM_* */
+  int32_t reserved;
 } b2ctr_uniform_gather_t;
+/* scatter_uniform_bwd: every (sample, feature) id is distinct (the ids are positions in a private row
+ * buffer, as on the row-sharded path): write scale*g instead of accumulating, no zero-fill needed. */
+#define B2CTR_UNIFORM_STORE_GRADS 1
 
 B2CTR_API b2ctr_status_t b2ctr_embed_gather_uniform_fwd(const b2ctr_uniform_gather_t* g,
                                                        int64_t batch, void* stream);

@@ -84,6 +84,7 @@ SIGNATURES = {
     "b2ctr_axpy": (_i32, [_vp, _vp, _f32, _i64, _vp]),
     "b2ctr_copy2d": (_i32, [_vp, _i64, _vp, _i64, _i64, _i64, _i32, _vp]),
     "b2ctr_rowsum": (_i32, [_vp, _i64, _vp, _i64, _i64, _vp]),
+    "b2ctr_pack_rows": (_i32, [_vp, C.POINTER(_i32), _i32, _i64, _vp, _i64, _vp]),
     "b2ctr_fill": (_i32, [_vp, _f32, _i64, _vp]),
     "b2ctr_mask_nonzero_and": (_i32, [_vp, _i32, _i64, _vp, _i32, _vp]),
     "b2ctr_mask_from_len": (_i32, [_vp, _i64, _i32, _vp, _vp]),

@@ -163,6 +163,25 @@ __global__ void mask_from_len_kernel(const int32_t* len, int64_t batch, int maxl
        i += (int64_t)gridDim.x * blockDim.x)
     out[i] = (int)(i % maxlen) < len[i / maxlen];
 }
+// Feeder: per-input contiguous host blocks [B, w_i] -> one row-major [B, total] pack on the device
+struct PackCols {
+  int64_t off[64];     // element offset of block i inside src
+  int32_t width[64];
+  int32_t col[64];     // first column of block i in dst
+  int32_t nblk, total;
+};
+__global__ void pack_rows_kernel(const float* __restrict__ src, const PackCols pc, int64_t batch, float* dst,
+                                 int64_t ld) {
+  const int64_t n = batch * pc.total;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n;
+       i += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t b = i / pc.total;
+    const int c = (int)(i - b * pc.total);
+    int k = 0;
+    while (k + 1 < pc.nblk && c >= pc.col[k + 1]) ++k;
+    dst[b * ld + c] = src[pc.off[k] + b * pc.width[k] + (c - pc.col[k])];
+  }
+}
 // one warp per row, lanes stride the columns; partials combined in a fixed shuffle tree
 __global__ void rowsum_kernel(const float* __restrict__ x, int64_t ld, float* out, int64_t rows,
                               int64_t cols) {
@@ -421,6 +440,26 @@ b2ctr_status_t b2ctr_copy2d(const float* src, int64_t ld_src, float* dst, int64_
     copy2d_kernel<false><<<grid_for(rows * cols, 256, 8), 256, 0, ST>>>(src, ld_src, dst, ld_dst, rows,
                                                                        cols, accumulate);
   B2_CHECK_LAUNCH("b2ctr_copy2d");
+  return B2CTR_OK;
+}
+
+b2ctr_status_t b2ctr_pack_rows(const float* src, const int32_t* widths, int32_t nblk, int64_t batch, float* dst,
+                               int64_t ld_dst, void* stream) {
+  B2_REQUIRE(src && widths && dst && nblk >= 1 && nblk <= 64, "pack_rows: need 1..64 blocks");
+  PackCols pc;
+  int64_t off = 0;
+  int col = 0;
+  for (int i = 0; i < nblk; ++i) {
+    B2_REQUIRE(widths[i] > 0, "pack_rows: width %d is not positive", i);
+    pc.off[i] = off; pc.width[i] = widths[i]; pc.col[i] = col;
+    off += (int64_t)widths[i] * batch;
+    col += widths[i];
+  }
+  pc.nblk = nblk; pc.total = col;
+  B2_REQUIRE(ld_dst >= col, "pack_rows: ld_dst < total width");
+  if (batch <= 0) return B2CTR_OK;
+  pack_rows_kernel<<<grid_for(batch * col, 256, 8), 256, 0, ST>>>(src, pc, batch, dst, ld_dst);
+  B2_CHECK_LAUNCH("b2ctr_pack_rows");
   return B2CTR_OK;
 }
 

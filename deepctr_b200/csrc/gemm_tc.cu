@@ -68,6 +68,15 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
 __device__ __forceinline__ uint64_t umma_desc(uint32_t saddr) {
   return (uint64_t)((saddr & 0x3FFFF) >> 4) | (1ull << 16) | (64ull << 32) | (1ull << 46) | (2ull << 61);
 }
+// MN-major, SWIZZLE_128B: the tile is a row of 64-element (128 B) atoms along M/N, each atom holding 64
+// k-rows of 128 B: LBO = atom stride (8192 B), SBO = stride between groups of 8 k-rows (1024 B).
+__device__ __forceinline__ uint64_t umma_desc_mn(uint32_t saddr) {
+  return (uint64_t)((saddr & 0x3FFFF) >> 4) | (512ull << 16) | (64ull << 32) | (1ull << 46) | (2ull << 61);
+}
+__device__ __forceinline__ uint64_t umma_desc_any(uint32_t base, int ks, int mn) {
+  // one UMMA K-step = 16 bf16 along K: 32 B inside the swizzled row (K-major) or 16 k-rows = 2048 B (MN-major)
+  return mn ? umma_desc_mn(base + ks * 2048) : umma_desc(base + ks * 32);
+}
 // kind::f16 instruction descriptor: D=f32, A=B=bf16, both K-major, N>>3 at bit 17, M>>4 at bit 24
 __device__ __forceinline__ uint32_t umma_idesc(int n) {
   return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(kTM >> 4) << 24);
@@ -347,8 +356,13 @@ static cudaError_t launch_tc(const TcArgs& ta, bool akc, bool bkc, cudaStream_t 
 // producers, not the tensor core, bound the kernel: every CTA re-converted both operand tiles.
 // ================================================================================================
 struct PlaneArgs {
-  const __nv_bfloat16* a_hi; const __nv_bfloat16* a_lo;   // [m_pad, k_pad]
-  const __nv_bfloat16* b_hi; const __nv_bfloat16* b_lo;   // [n_pad, k_pad]
+  // K-major planes: [rows_pad, k_pad] (k contiguous).  MN-major planes: [k_pad, rows_pad] (row index
+  // contiguous) - the natural layout of a row-major operand whose reduction dim is its row index
+  // (wgrad: X^T, dZ^T; forward: W).  *_pitch = elements between consecutive plane rows.
+  const __nv_bfloat16* a_hi; const __nv_bfloat16* a_lo;
+  const __nv_bfloat16* b_hi; const __nv_bfloat16* b_lo;
+  int64_t a_pitch, b_pitch;
+  int a_mn, b_mn;
   float* c; const float* bias; float* ws;
   int64_t m, n, k_pad;
   int64_t ldc;
@@ -475,17 +489,33 @@ __global__ void __launch_bounds__(kTcThreads, (STAGES * (2 * kTM * 128 + 2 * BN 
         const int64_t k0 = kbeg + (int64_t)kb * kTK;
 #pragma unroll
         for (int t = tid; t < kTM * 8; t += kProducerWarps * 32) {
-          const int r = t >> 3, c = t & 7;
-          const uint32_t off = r * 128 + ((c ^ (r & 7)) << 4);
-          const int64_t src = (m0 + r) * g.k_pad + k0 + c * 8;
+          uint32_t off;
+          int64_t src;
+          if (g.a_mn) {   // chunk c of k-row kk: 8 consecutive m inside atom c/8
+            const int kk = t / (kTM / 8), c = t % (kTM / 8);
+            off = (c >> 3) * 8192 + kk * 128 + (((c & 7) ^ (kk & 7)) << 4);
+            src = (k0 + kk) * g.a_pitch + m0 + c * 8;
+          } else {
+            const int r = t >> 3, c = t & 7;
+            off = r * 128 + ((c ^ (r & 7)) << 4);
+            src = (m0 + r) * g.a_pitch + k0 + c * 8;
+          }
           cp_async16(st + off, g.a_hi + src);
           cp_async16(st + A_PLANE + off, g.a_lo + src);
         }
 #pragma unroll
         for (int t = tid; t < BN * 8; t += kProducerWarps * 32) {
-          const int r = t >> 3, c = t & 7;
-          const uint32_t off = r * 128 + ((c ^ (r & 7)) << 4);
-          const int64_t src = (n0 + r) * g.k_pad + k0 + c * 8;
+          uint32_t off;
+          int64_t src;
+          if (g.b_mn) {
+            const int kk = t / (BN / 8), c = t % (BN / 8);
+            off = (c >> 3) * 8192 + kk * 128 + (((c & 7) ^ (kk & 7)) << 4);
+            src = (k0 + kk) * g.b_pitch + n0 + c * 8;
+          } else {
+            const int r = t >> 3, c = t & 7;
+            off = r * 128 + ((c ^ (r & 7)) << 4);
+            src = (n0 + r) * g.b_pitch + k0 + c * 8;
+          }
           cp_async16(st + 2 * A_PLANE + off, g.b_hi + src);
           cp_async16(st + 2 * A_PLANE + B_PLANE + off, g.b_lo + src);
         }
@@ -573,7 +603,7 @@ __global__ void __launch_bounds__(kTcThreads, (STAGES * (2 * kTM * 128 + 2 * BN 
     }
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
   } else {
-    const uint32_t idesc = umma_idesc(BN);
+    const uint32_t idesc = umma_idesc(BN) | (g.a_mn ? (1u << 15) : 0u) | (g.b_mn ? (1u << 16) : 0u);
     for (int kb = 0; kb < nkb; ++kb) {
       const int s = kb % STAGES;
       mbar_wait(&full_bar[s], (kb / STAGES) & 1);
@@ -583,10 +613,11 @@ __global__ void __launch_bounds__(kTcThreads, (STAGES * (2 * kTM * 128 + 2 * BN 
         const uint32_t a_hi = sa, a_lo = sa + A_PLANE, b_hi = sa + 2 * A_PLANE, b_lo = sa + 2 * A_PLANE + B_PLANE;
 #pragma unroll
         for (int ks = 0; ks < kTK / 16; ++ks) {
-          const uint32_t ko = ks * 32;
-          umma_f16(tmem_base, umma_desc(a_hi + ko), umma_desc(b_hi + ko), idesc, (kb | ks) ? 1u : 0u);
-          umma_f16(tmem_base, umma_desc(a_hi + ko), umma_desc(b_lo + ko), idesc, 1u);
-          umma_f16(tmem_base, umma_desc(a_lo + ko), umma_desc(b_hi + ko), idesc, 1u);
+          const uint64_t dah = umma_desc_any(a_hi, ks, g.a_mn), dal = umma_desc_any(a_lo, ks, g.a_mn);
+          const uint64_t dbh = umma_desc_any(b_hi, ks, g.b_mn), dbl = umma_desc_any(b_lo, ks, g.b_mn);
+          umma_f16(tmem_base, dah, dbh, idesc, (kb | ks) ? 1u : 0u);
+          umma_f16(tmem_base, dah, dbl, idesc, 1u);
+          umma_f16(tmem_base, dal, dbh, idesc, 1u);
         }
         umma_commit(&empty_bar[s]);
         if (kb == nkb - 1) umma_commit(&accum_bar);
@@ -624,20 +655,20 @@ static inline int planes_bn(int64_t n, int64_t k) {
 }
 
 static int tc_variant(const b2ctr_gemm_t* g) {
-  if (g->variant == 1 || g->variant == 2) return g->variant;
+  if (g->variant >= 1 && g->variant <= 3) return g->variant;
   static int mode = -1;
   if (mode < 0) {
     const char* ev = getenv("B2CTR_TC_VARIANT");
     mode = ev ? atoi(ev) : 2;
   }
-  return mode == 1 ? 1 : 2;
+  return (mode >= 1 && mode <= 3) ? mode : 2;
 }
 
 size_t gemm_bf16x3_workspace_bytes(const b2ctr_gemm_t* g) {
   size_t splitk = g->split_k > 1 ? (size_t)g->split_k * g->m * g->n * sizeof(float) : 0;
   if (tc_variant(g) == 1) return splitk;
   const int bn = planes_bn(g->n, g->k / (g->split_k > 1 ? g->split_k : 1));
-  const int64_t kp = round_up(g->k > 0 ? g->k : 1, kTK), mp = round_up(g->m, kTM), np = round_up(g->n, bn);
+  const int64_t kp = round_up(g->k > 0 ? g->k : 1, kTK), mp = round_up(g->m, kTM), np = round_up(g->n, 256);
   return splitk + (size_t)(mp + np) * kp * 2 * sizeof(__nv_bfloat16) + 512;
 }
 
@@ -658,24 +689,37 @@ static b2ctr_status_t gemm_planes(const b2ctr_gemm_t* g, void* workspace, size_t
   __nv_bfloat16* a_lo = a_hi + mp * kp;
   __nv_bfloat16* b_hi = a_lo + mp * kp;
   __nv_bfloat16* b_lo = b_hi + np * kp;
-  // operand splits (one streaming pass each)
-  auto split = [&](const float* p, bool k_contig, int64_t ld, int64_t rows, int64_t rows_pad,
-                   __nv_bfloat16* hi, __nv_bfloat16* lo) {
-    if (k_contig) {
-      const int vec = (ld % 4 == 0) && (((uintptr_t)p & 15) == 0);
-      split_planes_kernel<<<grid_for(rows_pad * (kp / 8), 256, 8), 256, 0, st>>>(p, ld, rows, g->k, rows_pad, kp,
-                                                                               hi, lo, vec);
-    } else {
-      dim3 grid((unsigned)ceil_div(rows_pad, 64), (unsigned)(kp / 64));
-      split_planes_t_kernel<<<grid, 256, 0, st>>>(p, ld, rows, g->k, rows_pad, kp, hi, lo);
-    }
+  // operand splits (one streaming pass each).  variant 2: always K-major planes (row-contiguous sources go
+  // through a transposing split); variant 3: row-contiguous sources keep their layout (MN-major planes)
+  // and the UMMA descriptors do the transposition - the same planes then serve every GEMM that reads the
+  // tensor (forward / dgrad / wgrad).
+  const bool mn_ok = tc_variant(g) == 3;
+  const bool a_kc = !g->trans_a, b_kc = g->trans_b != 0;
+  const int a_mn = (!a_kc && mn_ok) ? 1 : 0;
+  const int b_mn = (!b_kc && mn_ok && bn >= 64) ? 1 : 0;   // an MN-major atom is 64 elements wide
+  auto split_k = [&](const float* p, int64_t ld, int64_t rows, int64_t cols, int64_t rows_pad, int64_t cols_pad,
+                     __nv_bfloat16* hi, __nv_bfloat16* lo) {      // planes[r, c] = p[r*ld + c]
+    const int vec = (ld % 4 == 0) && (((uintptr_t)p & 15) == 0);
+    split_planes_kernel<<<grid_for(rows_pad * (cols_pad / 8), 256, 8), 256, 0, st>>>(p, ld, rows, cols, rows_pad,
+                                                                                   cols_pad, hi, lo, vec);
   };
-  split(g->a, !g->trans_a, g->lda, g->m, mp, a_hi, a_lo);
+  auto split_t = [&](const float* p, int64_t ld, int64_t rows, int64_t rows_pad, __nv_bfloat16* hi,
+                     __nv_bfloat16* lo) {                        // planes[r, k] = p[k*ld + r]
+    dim3 grid((unsigned)ceil_div(rows_pad, 64), (unsigned)(kp / 64));
+    split_planes_t_kernel<<<grid, 256, 0, st>>>(p, ld, rows, g->k, rows_pad, kp, hi, lo);
+  };
+  if (a_kc) split_k(g->a, g->lda, g->m, g->k, mp, kp, a_hi, a_lo);
+  else if (a_mn) split_k(g->a, g->lda, g->k, g->m, kp, mp, a_hi, a_lo);
+  else split_t(g->a, g->lda, g->m, mp, a_hi, a_lo);
   B2_CHECK_LAUNCH("b2ctr_gemm(bf16x3 split A)");
-  split(g->b, g->trans_b != 0, g->ldb, g->n, np, b_hi, b_lo);
+  if (b_kc) split_k(g->b, g->ldb, g->n, g->k, np, kp, b_hi, b_lo);
+  else if (b_mn) split_k(g->b, g->ldb, g->k, g->n, kp, np, b_hi, b_lo);
+  else split_t(g->b, g->ldb, g->n, np, b_hi, b_lo);
   B2_CHECK_LAUNCH("b2ctr_gemm(bf16x3 split B)");
   PlaneArgs pa;
   pa.a_hi = a_hi; pa.a_lo = a_lo; pa.b_hi = b_hi; pa.b_lo = b_lo;
+  pa.a_mn = a_mn; pa.b_mn = b_mn;
+  pa.a_pitch = a_mn ? mp : kp; pa.b_pitch = b_mn ? np : kp;
   pa.c = g->c; pa.bias = g->bias; pa.ws = ws;
   pa.m = g->m; pa.n = g->n; pa.k_pad = kp; pa.ldc = g->ldc;
   pa.k_per_split = ceil_div(ceil_div(kp, splits), kTK) * kTK;

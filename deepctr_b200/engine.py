@@ -804,6 +804,10 @@ def Adagrad(learning_rate=1e-3, **kw):
     return Optimizer("adagrad", kw.get("lr", learning_rate))
 
 
+def E_labels(t):
+    return t
+
+
 class History(object):
     def __init__(self):
         self.history = {}
@@ -989,14 +993,35 @@ class Model(object):
         out = self.outputs if isinstance(self.outputs, KTensor) else self.outputs[0]
         return contiguous(vals[id(out)]).reshape(-1, 1)
 
-    def _loss_step(self, x, y, train):
+    def _stage_batch(self, x, y, stream=None):
+        """Pack + H2D one batch (optionally on a side stream); returns (feed, labels, ready event)."""
+        if stream is None:
+            return self._feed(x), self._feeder.labels(y), None
+        with torch.cuda.stream(stream):
+            feed = self._feed(x)
+            labels = self._feeder.labels(y)
+            ev = torch.cuda.Event()
+            ev.record(stream)
+        return feed, labels, ev
+
+    def _loss_step(self, x, y, train, staged=None):
         """forward (+ backward + update when ``train``); returns the device loss_sum tensor [1] and
         batch size - no host synchronisation here."""
         if self.optimizer is None:
             raise RuntimeError("You must compile your model before training/testing.")
         self._materialize()
-        feed = self._feed(x)
-        labels = self._feeder.labels(y)
+        if staged is None:
+            feed = self._feed(x)
+            labels = self._feeder.labels(y)
+        else:
+            feed, labels, ev = staged
+            if ev is not None:
+                cur = torch.cuda.current_stream()
+                cur.wait_event(ev)
+                for v in list(feed.values()) + [E_labels(labels)]:   # staged on a side stream: tell the allocator
+                    t = v.data if isinstance(v, Var) else v
+                    if t is not None and t.is_cuda:
+                        t.record_stream(cur)
         logit_t, head = self._head()
         if head is None:
             raise ValueError("training needs a PredictionLayer output (all builders end with one)")
@@ -1103,9 +1128,31 @@ class Model(object):
                 host_losses = host_losses.pin_memory()
             except Exception:
                 pass
-            for i, s in enumerate(range(0, n, batch_size)):
+            # batch i+1 is packed and copied H2D by a helper thread on a side stream while the kernels of
+            # batch i are being launched / run
+            from concurrent.futures import ThreadPoolExecutor
+            if not hasattr(self, "_stage_pool"):
+                self._stage_pool = ThreadPoolExecutor(1)
+                self._stage_stream = torch.cuda.Stream()
+            starts = list(range(0, n, batch_size))
+
+            def batch_of(s):
                 idx = perm[s:s + batch_size] if perm is not None else slice(s, min(n, s + batch_size))
-                ls, _, b = self._loss_step(slice_inputs(x, idx), y[idx], True)
+                return slice_inputs(x, idx), y[idx]
+
+            self._materialize()
+            dev_index = torch.cuda.current_device()
+
+            def stage(s):
+                torch.cuda.set_device(dev_index)
+                bx, by = batch_of(s)
+                return self._stage_batch(bx, by, self._stage_stream)
+
+            fut = self._stage_pool.submit(stage, starts[0]) if starts else None
+            for i, s in enumerate(starts):
+                staged = fut.result()
+                fut = self._stage_pool.submit(stage, starts[i + 1]) if i + 1 < len(starts) else None
+                ls, _, b = self._loss_step(None, None, True, staged=staged)
                 host_losses[i:i + 1].copy_(ls, non_blocking=True)
                 cnt += b
             torch.cuda.synchronize()

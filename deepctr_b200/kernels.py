@@ -239,6 +239,16 @@ def copy2d(src, ld_src, dst, ld_dst, rows, cols, accumulate=False, src_off=0, ds
     return dst
 
 
+def pack_rows(src_flat, widths, batch):
+    """[sum_i B*w_i] flat blocks -> row-major [B, sum w_i]."""
+    _require_cuda(src_flat)
+    total = int(sum(widths))
+    out = torch.empty((batch, total), dtype=torch.float32, device=src_flat.device)
+    arr = (C.c_int32 * len(widths))(*[int(w) for w in widths])
+    L.check(L.lib().b2ctr_pack_rows(ptr(src_flat), arr, len(widths), batch, ptr(out), total, stream()), "pack_rows")
+    return out
+
+
 def rowsum(x, rows, cols, ld=None):
     _require_cuda(x)
     out = torch.empty((rows,), dtype=torch.float32, device=x.device)

@@ -208,6 +208,10 @@ B2CTR_API b2ctr_status_t b2ctr_axpy(const float* x, float* y, float alpha, int64
 /* strided 2-D copy: dst[r*ld_dst + c] (+)= src[r*ld_src + c], r<rows, c<cols  (concat / slice)  */
 B2CTR_API b2ctr_status_t b2ctr_copy2d(const float* src, int64_t ld_src, float* dst, int64_t ld_dst,
                                      int64_t rows, int64_t cols, int32_t accumulate, void* stream);
+/* input staging: src holds nblk contiguous blocks, block i = [batch, widths[i]] row-major; dst[b, :] is
+ * their row-wise concatenation (the dense-feature pack, deepctr/inputs.py:161-172 + layers/utils.py:336-346) */
+B2CTR_API b2ctr_status_t b2ctr_pack_rows(const float* src, const int32_t* widths, int32_t nblk, int64_t batch,
+                                        float* dst, int64_t ld_dst, void* stream);
 /* out[r] = sum_c x[r*ld + c] (ascending c, fp32)   (Linear mode 0/2, layers/utils.py:160-171) */
 B2CTR_API b2ctr_status_t b2ctr_rowsum(const float* x, int64_t ld, float* out, int64_t rows,
                                      int64_t cols, void* stream);

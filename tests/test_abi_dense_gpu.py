@@ -180,7 +180,7 @@ def test_optimizers(cuda):
 @pytest.mark.parametrize("m,n,k", [(128, 128, 64), (1, 1, 1), (257, 256, 845), (130, 64, 128), (1000, 1, 64),
                                    (64, 300, 7), (4096, 256, 848), (300, 40, 200)])
 @pytest.mark.parametrize("ta,tb", [(False, False), (False, True), (True, False), (True, True)])
-@pytest.mark.parametrize("variant", [1, 2])      # 1: split inside the GEMM producers, 2: pre-split planes
+@pytest.mark.parametrize("variant", [1, 2, 3])   # 1: split in the GEMM producers, 2: K-major planes, 3: + MN-major
 def test_gemm_bf16x3_tensor_core(cuda, m, n, k, ta, tb, variant):
     """tcgen05 split-bf16 GEMM: error bound ~2^-16 relative to sum |a||b|."""
     K, L = _kern()
@@ -197,7 +197,7 @@ def test_gemm_bf16x3_tensor_core(cuda, m, n, k, ta, tb, variant):
     assert ((got - want).abs() <= bound).all(), float(((got - want).abs() / bound).max())
 
 
-@pytest.mark.parametrize("variant", [1, 2])
+@pytest.mark.parametrize("variant", [1, 2, 3])
 def test_gemm_bf16x3_splitk_accumulate(cuda, variant):
     K, L = _kern()
     rng = np.random.RandomState(77)

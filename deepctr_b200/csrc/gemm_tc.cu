@@ -747,7 +747,7 @@ static b2ctr_status_t gemm_planes(const b2ctr_gemm_t* g, void* workspace, size_t
 
 b2ctr_status_t gemm_bf16x3(const b2ctr_gemm_t* g, void* workspace, size_t workspace_bytes,
                            cudaStream_t st) {
-  if (tc_variant(g) == 2) return gemm_planes(g, workspace, workspace_bytes, st);
+  if (tc_variant(g) >= 2) return gemm_planes(g, workspace, workspace_bytes, st);
   TcArgs ta;
   ta.a = g->a; ta.b = g->b; ta.c = g->c; ta.bias = g->bias; ta.ws = (float*)workspace;
   ta.m = g->m; ta.n = g->n; ta.k = g->k;

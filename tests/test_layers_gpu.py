@@ -306,3 +306,58 @@ def test_hash_layer_device_and_vocabulary(cuda, tmp_path):
     p.write_text("1,lake\n2,merson\n3,johnson\n")
     out = Hash(num_buckets=4, vocabulary_path=str(p))([["lake"], ["johnson"], ["lakemerson"]])
     assert np.array_equal(np.asarray(out), [[1], [3], [0]])
+
+
+@pytest.mark.parametrize("training", [False, True])
+def test_dnn_with_batchnorm(cuda, training):
+    """DNN(use_bn=True): tensordot + bias -> BatchNormalization -> activation (layers/core.py:193-200)."""
+    from deepctr_b200.layers import DNN
+    rng = np.random.RandomState(31)
+    x = rng.normal(size=(77, 6)).astype(np.float32)
+    layer = DNN((5, 4), activation="relu", use_bn=True, seed=2)
+    layer.build((None, 6))
+    H.randomize_weights(layer, rng, 0.5)
+    bn_before = [{"gamma": _t(b.gamma.value()), "beta": _t(b.beta.value()),
+                  "moving_mean": _t(b.moving_mean.value(), False), "moving_var": _t(b.moving_variance.value(), False)}
+                 for b in layer.bn_layers]
+    out, gy, gin, gw = _run(layer, x, rng, training=training)
+    xt = _t(x)
+    ks = [_t(w.value()) for w in layer.kernels]
+    bs = [_t(w.value()) for w in layer.bias]
+    want = O.dnn(xt, ks, bs, "relu", None, None, training, bn_params=bn_before)
+    (want * _t(gy, False)).sum().backward()
+    _close(out, want.detach(), 3e-4, 3e-5)
+    _close(gin[0], xt.grad, 1e-3, 1e-4)
+    for i in range(2):
+        _close(gw["kernel%d" % i], ks[i].grad, 1e-3, 1e-4)
+        _close(gw["bn%d/gamma" % i], bn_before[i]["gamma"].grad, 1e-3, 1e-4)
+        _close(gw["bn%d/beta" % i], bn_before[i]["beta"].grad, 1e-3, 1e-4)
+    if training:   # moving statistics moved towards the batch statistics with momentum 0.99
+        h0 = (xt.detach() @ ks[0].detach() + bs[0].detach())
+        np.testing.assert_allclose(layer.bn_layers[0].moving_mean.value(),
+                                   0.99 * bn_before[0]["moving_mean"].numpy() + 0.01 * h0.mean(0).numpy(),
+                                   rtol=1e-4, atol=1e-5)
+
+
+def test_dropout_mask_is_consistent_between_forward_and_backward(cuda):
+    from deepctr_b200 import engine as E, ops
+    rng = np.random.RandomState(32)
+    x = E.to_var(np.ones((4096, 16), np.float32))
+    x.requires_grad = True
+    tape = E.Tape()
+    with E.recording(tape):
+        y = ops.dropout(x, 0.25, seed=7)
+    yv = y.data.cpu().numpy()
+    kept = yv != 0
+    assert abs(kept.mean() - 0.75) < 0.02
+    np.testing.assert_allclose(yv[kept], 1.0 / 0.75, rtol=1e-6)
+    E.add_grad(y, torch.ones_like(y.data))
+    tape.backward()
+    g = x.grad.cpu().numpy()
+    assert np.array_equal(g != 0, kept) and np.allclose(g[kept], 1.0 / 0.75)
+    # inference: identity
+    from deepctr_b200.layers import DNN
+    layer = DNN((8,), dropout_rate=0.5)
+    a = layer(np.ones((10, 4), np.float32)).data.cpu().numpy()
+    b = layer(np.ones((10, 4), np.float32)).data.cpu().numpy()
+    assert np.array_equal(a, b)

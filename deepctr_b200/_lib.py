@@ -57,7 +57,7 @@ class Gemm(C.Structure):
                 ("lda", C.c_int64), ("ldb", C.c_int64), ("ldc", C.c_int64),
                 ("trans_a", C.c_int32), ("trans_b", C.c_int32), ("act", C.c_int32),
                 ("accumulate", C.c_int32), ("precision", C.c_int32), ("split_k", C.c_int32),
-                ("alpha", C.c_float), ("variant", C.c_int32)]
+                ("alpha", C.c_float), ("variant", C.c_int32), ("a_planes", C.c_void_p), ("b_planes", C.c_void_p)]
 
 
 _vp, _i32, _i64, _f32, _sz, _u64 = C.c_void_p, C.c_int32, C.c_int64, C.c_float, C.c_size_t, C.c_uint64
@@ -77,6 +77,8 @@ SIGNATURES = {
     "b2ctr_init_normal": (_i32, [_vp, _i64, _f32, _f32, _u64, _vp]),
     "b2ctr_gemm_workspace_bytes": (_sz, [C.POINTER(Gemm)]),
     "b2ctr_gemm": (_i32, [C.POINTER(Gemm), _vp, _sz, _vp]),
+    "b2ctr_planes_bytes": (_sz, [_i64, _i64]),
+    "b2ctr_split_planes": (_i32, [_vp, _i64, _i64, _i64, _vp, _vp]),
     "b2ctr_bias_act_bwd_workspace_bytes": (_sz, [_i64, _i64]),
     "b2ctr_bias_act_bwd": (_i32, [_vp, _vp, _vp, _vp, _i64, _i64, _i64, _i32, _vp, _sz, _vp]),
     "b2ctr_act_fwd": (_i32, [_vp, _vp, _i64, _i32, _vp]),

@@ -182,6 +182,9 @@ b2ctr_status_t gemm_fp32(const b2ctr_gemm_t* g, void* workspace, size_t workspac
 b2ctr_status_t gemm_bf16x3(const b2ctr_gemm_t* g, void* workspace, size_t workspace_bytes,
                            cudaStream_t st);  // gemm_tc.cu
 size_t gemm_bf16x3_workspace_bytes(const b2ctr_gemm_t* g);
+size_t planes_bytes(int64_t rows, int64_t cols);
+b2ctr_status_t split_planes(const float* src, int64_t ld, int64_t rows, int64_t cols, void* planes,
+                            cudaStream_t st);
 
 }  // namespace b2ctr
 
@@ -193,6 +196,15 @@ size_t b2ctr_gemm_workspace_bytes(const b2ctr_gemm_t* g) {
   if (!g) return 0;
   if (g->precision == B2CTR_GEMM_BF16X3) return gemm_bf16x3_workspace_bytes(g);
   return g->split_k > 1 ? (size_t)g->split_k * g->m * g->n * sizeof(float) : 0;
+}
+
+size_t b2ctr_planes_bytes(int64_t rows, int64_t cols) { return planes_bytes(rows, cols); }
+
+b2ctr_status_t b2ctr_split_planes(const float* src, int64_t ld, int64_t rows, int64_t cols, void* planes,
+                                  void* stream) {
+  B2_REQUIRE(src && planes && rows > 0 && cols > 0 && ld >= cols, "split_planes: bad arguments");
+  B2_REQUIRE(((uintptr_t)planes & 15) == 0, "split_planes: planes must be 16-byte aligned");
+  return split_planes(src, ld, rows, cols, planes, (cudaStream_t)stream);
 }
 
 b2ctr_status_t b2ctr_gemm(const b2ctr_gemm_t* g, void* workspace, size_t workspace_bytes,

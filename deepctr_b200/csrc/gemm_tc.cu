@@ -659,9 +659,9 @@ static int tc_variant(const b2ctr_gemm_t* g) {
   static int mode = -1;
   if (mode < 0) {
     const char* ev = getenv("B2CTR_TC_VARIANT");
-    mode = ev ? atoi(ev) : 2;
+    mode = ev ? atoi(ev) : 3;
   }
-  return (mode >= 1 && mode <= 3) ? mode : 2;
+  return (mode >= 1 && mode <= 3) ? mode : 3;
 }
 
 size_t gemm_bf16x3_workspace_bytes(const b2ctr_gemm_t* g) {
@@ -679,24 +679,28 @@ static b2ctr_status_t gemm_planes(const b2ctr_gemm_t* g, void* workspace, size_t
     return B2CTR_ERR_WORKSPACE;
   }
   const int splits = g->split_k > 1 ? g->split_k : 1;
-  const int bn = planes_bn(g->n, g->k / (g->split_k > 1 ? g->split_k : 1));
-  const int64_t kp = round_up(g->k > 0 ? g->k : 1, kTK), mp = round_up(g->m, kTM), np = round_up(g->n, bn);
+  int bn = planes_bn(g->n, g->k / (g->split_k > 1 ? g->split_k : 1));
+  const int64_t kp = round_up(g->k > 0 ? g->k : 1, kTK), mp = round_up(g->m, kTM);
   unsigned char* w = (unsigned char*)workspace;
   float* ws = (float*)w;
   w += splits > 1 ? (size_t)splits * g->m * g->n * sizeof(float) : 0;
   w = (unsigned char*)(((uintptr_t)w + 255) & ~(uintptr_t)255);
-  __nv_bfloat16* a_hi = (__nv_bfloat16*)w;
-  __nv_bfloat16* a_lo = a_hi + mp * kp;
-  __nv_bfloat16* b_hi = a_lo + mp * kp;
-  __nv_bfloat16* b_lo = b_hi + np * kp;
-  // operand splits (one streaming pass each).  variant 2: always K-major planes (row-contiguous sources go
-  // through a transposing split); variant 3: row-contiguous sources keep their layout (MN-major planes)
-  // and the UMMA descriptors do the transposition - the same planes then serve every GEMM that reads the
-  // tensor (forward / dgrad / wgrad).
+  // variant 2: always K-major planes (row-contiguous sources go through a transposing split);
+  // variant 3: row-contiguous sources keep their layout (MN-major planes) and the UMMA descriptors do the
+  // transposition - the same planes then serve every GEMM that reads the tensor (forward / dgrad / wgrad),
+  // which is what caller-provided planes (g->a_planes / g->b_planes) exploit.
   const bool mn_ok = tc_variant(g) == 3;
   const bool a_kc = !g->trans_a, b_kc = g->trans_b != 0;
-  const int a_mn = (!a_kc && mn_ok) ? 1 : 0;
-  const int b_mn = (!b_kc && mn_ok && bn >= 64) ? 1 : 0;   // an MN-major atom is 64 elements wide
+  const int64_t a_sr = g->trans_a ? g->k : g->m, a_sc = g->trans_a ? g->m : g->k;   // stored rows / cols
+  const int64_t b_sr = g->trans_b ? g->n : g->k, b_sc = g->trans_b ? g->k : g->n;
+  const bool a_given = g->a_planes && (a_kc || mn_ok);
+  bool b_given = g->b_planes && (b_kc || (mn_ok && bn >= 64));
+  if (b_given && !b_kc && round_up(b_sc, 128) % bn != 0) bn = 128;   // MN-major tiles must stay inside the pad
+  const int64_t np = round_up(g->n, bn);
+  const int a_mn = a_given ? !a_kc : ((!a_kc && mn_ok) ? 1 : 0);
+  const int b_mn = b_given ? !b_kc : ((!b_kc && mn_ok && bn >= 64) ? 1 : 0);   // an MN atom is 64 elements wide
+  __nv_bfloat16 *a_hi, *a_lo, *b_hi, *b_lo;
+  int64_t a_pitch, b_pitch;
   auto split_k = [&](const float* p, int64_t ld, int64_t rows, int64_t cols, int64_t rows_pad, int64_t cols_pad,
                      __nv_bfloat16* hi, __nv_bfloat16* lo) {      // planes[r, c] = p[r*ld + c]
     const int vec = (ld % 4 == 0) && (((uintptr_t)p & 15) == 0);
@@ -708,18 +712,32 @@ static b2ctr_status_t gemm_planes(const b2ctr_gemm_t* g, void* workspace, size_t
     dim3 grid((unsigned)ceil_div(rows_pad, 64), (unsigned)(kp / 64));
     split_planes_t_kernel<<<grid, 256, 0, st>>>(p, ld, rows, g->k, rows_pad, kp, hi, lo);
   };
-  if (a_kc) split_k(g->a, g->lda, g->m, g->k, mp, kp, a_hi, a_lo);
-  else if (a_mn) split_k(g->a, g->lda, g->k, g->m, kp, mp, a_hi, a_lo);
-  else split_t(g->a, g->lda, g->m, mp, a_hi, a_lo);
-  B2_CHECK_LAUNCH("b2ctr_gemm(bf16x3 split A)");
-  if (b_kc) split_k(g->b, g->ldb, g->n, g->k, np, kp, b_hi, b_lo);
-  else if (b_mn) split_k(g->b, g->ldb, g->k, g->n, kp, np, b_hi, b_lo);
-  else split_t(g->b, g->ldb, g->n, np, b_hi, b_lo);
-  B2_CHECK_LAUNCH("b2ctr_gemm(bf16x3 split B)");
+  if (a_given) {
+    const int64_t rp = round_up(a_sr, 256), cp = round_up(a_sc, 128);
+    a_hi = (__nv_bfloat16*)g->a_planes; a_lo = a_hi + rp * cp; a_pitch = cp;
+  } else {
+    a_hi = (__nv_bfloat16*)w; a_lo = a_hi + mp * kp; w = (unsigned char*)(a_lo + mp * kp);
+    a_pitch = a_mn ? mp : kp;
+    if (a_kc) split_k(g->a, g->lda, g->m, g->k, mp, kp, a_hi, a_lo);
+    else if (a_mn) split_k(g->a, g->lda, g->k, g->m, kp, mp, a_hi, a_lo);
+    else split_t(g->a, g->lda, g->m, mp, a_hi, a_lo);
+    B2_CHECK_LAUNCH("b2ctr_gemm(bf16x3 split A)");
+  }
+  if (b_given) {
+    const int64_t rp = round_up(b_sr, 256), cp = round_up(b_sc, 128);
+    b_hi = (__nv_bfloat16*)g->b_planes; b_lo = b_hi + rp * cp; b_pitch = cp;
+  } else {
+    b_hi = (__nv_bfloat16*)w; b_lo = b_hi + np * kp;
+    b_pitch = b_mn ? np : kp;
+    if (b_kc) split_k(g->b, g->ldb, g->n, g->k, np, kp, b_hi, b_lo);
+    else if (b_mn) split_k(g->b, g->ldb, g->k, g->n, kp, np, b_hi, b_lo);
+    else split_t(g->b, g->ldb, g->n, np, b_hi, b_lo);
+    B2_CHECK_LAUNCH("b2ctr_gemm(bf16x3 split B)");
+  }
   PlaneArgs pa;
   pa.a_hi = a_hi; pa.a_lo = a_lo; pa.b_hi = b_hi; pa.b_lo = b_lo;
   pa.a_mn = a_mn; pa.b_mn = b_mn;
-  pa.a_pitch = a_mn ? mp : kp; pa.b_pitch = b_mn ? np : kp;
+  pa.a_pitch = a_pitch; pa.b_pitch = b_pitch;
   pa.c = g->c; pa.bias = g->bias; pa.ws = ws;
   pa.m = g->m; pa.n = g->n; pa.k_pad = kp; pa.ldc = g->ldc;
   pa.k_per_split = ceil_div(ceil_div(kp, splits), kTK) * kTK;
@@ -742,6 +760,20 @@ static b2ctr_status_t gemm_planes(const b2ctr_gemm_t* g, void* workspace, size_t
     tc_splitk_reduce_kernel<<<grid_for(g->m * g->n, 256, 4), 256, 0, st>>>(ta);
     B2_CHECK_LAUNCH("b2ctr_gemm(bf16x3 splitk_reduce)");
   }
+  return B2CTR_OK;
+}
+
+size_t planes_bytes(int64_t rows, int64_t cols) {
+  return (size_t)round_up(rows, 256) * round_up(cols, 128) * 2 * sizeof(__nv_bfloat16);
+}
+b2ctr_status_t split_planes(const float* src, int64_t ld, int64_t rows, int64_t cols, void* planes,
+                            cudaStream_t st) {
+  const int64_t rp = round_up(rows, 256), cp = round_up(cols, 128);
+  __nv_bfloat16* hi = (__nv_bfloat16*)planes;
+  const int vec = (ld % 4 == 0) && (((uintptr_t)src & 15) == 0);
+  split_planes_kernel<<<grid_for(rp * (cp / 8), 256, 8), 256, 0, st>>>(src, ld, rows, cols, rp, cp, hi, hi + rp * cp,
+                                                                      vec);
+  B2_CHECK_LAUNCH("b2ctr_split_planes");
   return B2CTR_OK;
 }
 

@@ -143,7 +143,8 @@ def init_normal(dst, mean, std, seed):
 
 # ---- GEMM -----------------------------------------------------------------------------------
 def gemm(a, b, c=None, bias=None, trans_a=False, trans_b=False, act=L.ACT_NONE, accumulate=False,
-         precision=L.GEMM_FP32, split_k=1, alpha=1.0, m=None, n=None, k=None, variant=0):
+         precision=L.GEMM_FP32, split_k=1, alpha=1.0, m=None, n=None, k=None, variant=0, a_planes=None,
+         b_planes=None):
     """C[M,N] = act(alpha * op(A) @ op(B) + bias) on 2-D row-major (possibly ld-padded) tensors."""
     _require_cuda(a, b, c, bias)
     if m is None:
@@ -162,10 +163,22 @@ def gemm(a, b, c=None, bias=None, trans_a=False, trans_b=False, act=L.ACT_NONE, 
     g.trans_a, g.trans_b = int(trans_a), int(trans_b)
     g.act, g.accumulate, g.precision, g.split_k, g.alpha = act, int(accumulate), precision, split_k, alpha
     g.variant = variant
+    g.a_planes = a_planes.data_ptr() if a_planes is not None else None
+    g.b_planes = b_planes.data_ptr() if b_planes is not None else None
     nbytes = L.lib().b2ctr_gemm_workspace_bytes(C.byref(g))
     ws = workspace(nbytes, a.device)
     L.check(L.lib().b2ctr_gemm(C.byref(g), ptr(ws), nbytes if ws is not None else 0, stream()), "gemm")
     return c
+
+
+def split_planes(x2d):
+    """bf16 hi/lo planes of a 2-D fp32 tensor (row stride may exceed the width) for BF16X3 GEMMs."""
+    _require_cuda(x2d)
+    rows, cols = x2d.shape
+    nbytes = L.lib().b2ctr_planes_bytes(rows, cols)
+    buf = torch.empty((nbytes,), dtype=torch.uint8, device=x2d.device)
+    L.check(L.lib().b2ctr_split_planes(ptr(x2d), x2d.stride(0), rows, cols, ptr(buf), stream()), "split_planes")
+    return buf
 
 
 # ---- elementwise ----------------------------------------------------------------------------
@@ -345,7 +358,7 @@ def profile_summary():
     return out
 
 
-for _n in ("embed_gather_fwd", "embed_scatter_add", "embed_gather_uniform_fwd", "embed_scatter_uniform_bwd",
+for _n in ("split_planes", "embed_gather_fwd", "embed_scatter_add", "embed_gather_uniform_fwd", "embed_scatter_uniform_bwd",
            "hash64", "gemm", "bias_act_bwd", "act_fwd", "add_n", "axpy", "fill", "copy2d", "rowsum", "fm_fwd",
            "fm_bwd", "predict_loss", "sgd_step", "adam_step", "adagrad_step", "mask_nonzero_and",
            "mask_from_len"):

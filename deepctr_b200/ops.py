@@ -12,6 +12,11 @@ from . import engine as E
 GEMM_PRECISION = L.GEMM_FP32
 
 
+# BF16X3: split every GEMM operand into bf16 planes once per step and reuse them (needs MN-major operands,
+# i.e. tc variant 3)
+PLANE_REUSE = True
+
+
 def set_gemm_precision(mode):
     """'fp32' (exact FFMA) or 'bf16x3' (tcgen05 split-bf16, ~2^-17 relative)."""
     global GEMM_PRECISION
@@ -41,6 +46,15 @@ def _as2d(x):
 
 
 # ---- GEMM based --------------------------------------------------------------------------------
+def _planes_of(var, t2):
+    """bf16 hi/lo planes of a Var's 2-D view, split once per step and shared by every GEMM that reads it
+    (forward of each consumer + the wgrad GEMMs)."""
+    key = (t2.data_ptr(), tuple(t2.shape), t2.stride(0))
+    if var.planes is None or var.planes[0] != key:
+        var.planes = (key, K.split_planes(t2))
+    return var.planes[1]
+
+
 def dense(x, w, b=None, activation=None):
     """y = act(x @ w + b) over the last axis (tf.tensordot(x, w, axes=(-1, 0)) + bias_add)."""
     act = L.ACT_BY_NAME.get(activation, None)
@@ -50,7 +64,12 @@ def dense(x, w, b=None, activation=None):
     n = w.shape[1]
     wd = w.materialize() if isinstance(w, E.Weight) else w.data
     bd = (b.materialize() if isinstance(b, E.Weight) else b.data) if b is not None else None
-    y = K.gemm(x2, wd, bias=bd, act=fused_act, precision=GEMM_PRECISION, m=m, n=n, k=kdim)
+    # BF16X3: operands are split into bf16 planes once and the planes are reused by forward/dgrad/wgrad
+    reuse = GEMM_PRECISION == L.GEMM_BF16X3 and PLANE_REUSE and m >= 128
+    xp = _planes_of(x, x2) if reuse else None
+    wp = K.split_planes(wd) if reuse else None
+    y = K.gemm(x2, wd, bias=bd, act=fused_act, precision=GEMM_PRECISION, m=m, n=n, k=kdim, a_planes=xp,
+               b_planes=wp)
     out = E.Var(y.reshape(tuple(x.data.shape[:-1]) + (n,)))
     if act is None and activation is not None:
         raise ValueError("activation %r cannot be fused into dense(); apply it as a layer" % activation)
@@ -66,6 +85,7 @@ def dense(x, w, b=None, activation=None):
                 dz = dy
         else:
             dz, db = dy, None
+        dzp = K.split_planes(dz) if reuse and (x.requires_grad or w.requires_grad) else None
         if x.requires_grad:
             base = x.base
             if (base is not None and x.col0 == 0 and x.ncols != -1 and base.data.dim() == 2
@@ -75,14 +95,16 @@ def dense(x, w, b=None, activation=None):
                 ld = base.data.stride(0)
                 buf = _empty((m, ld), dy)
                 dxw = buf[:, :kdim]
-                K.gemm(dz, wd, c=dxw, trans_b=True, precision=GEMM_PRECISION, m=m, n=kdim, k=n)
+                K.gemm(dz, wd, c=dxw, trans_b=True, precision=GEMM_PRECISION, m=m, n=kdim, k=n, a_planes=dzp,
+                       b_planes=wp)
                 E.add_grad(x, dxw)
             else:
-                dx = K.gemm(dz, wd, trans_b=True, precision=GEMM_PRECISION, m=m, n=kdim, k=n)
+                dx = K.gemm(dz, wd, trans_b=True, precision=GEMM_PRECISION, m=m, n=kdim, k=n, a_planes=dzp,
+                            b_planes=wp)
                 E.add_grad(x, dx.reshape(x.data.shape))
         if w.requires_grad:
             dw = K.gemm(x2, dz, trans_a=True, precision=GEMM_PRECISION, split_k=_split_k(kdim, n, m),
-                        m=kdim, n=n, k=m)
+                        m=kdim, n=n, k=m, a_planes=xp, b_planes=dzp)
             E.add_grad(w, dw)
         if need_db:
             E.add_grad(b, db)

@@ -181,8 +181,16 @@ typedef struct b2ctr_gemm {
   int32_t precision;       /* B2CTR_GEMM_*                                                     */
   int32_t split_k;         /* >1: split the K loop over this many CTAs (needs workspace)       */
   float alpha;             /* scales op(A)@op(B)                                               */
-  int32_t variant;         /* BF16X3 only: 0 default, 1 in-kernel split, 2 pre-split planes (testing)  */
+  int32_t variant;         /* BF16X3 only: 0 default, 1 in-kernel split, 2 K-major planes, 3 + MN-major */
+  const void* a_planes;    /* optional: b2ctr_split_planes() of the STORED a / b matrix.  Lets one split */
+  const void* b_planes;    /* serve every GEMM that reads the tensor (forward, dgrad, wgrad); BF16X3 only */
 } b2ctr_gemm_t;
+
+/* bf16 (hi, lo) planes of an fp32 matrix [rows, cols]: hi = bf16(x), lo = bf16(x - hi), zero padded to
+ * [round_up(rows,256), round_up(cols,128)]; the buffer holds the hi plane followed by the lo plane. */
+B2CTR_API size_t b2ctr_planes_bytes(int64_t rows, int64_t cols);
+B2CTR_API b2ctr_status_t b2ctr_split_planes(const float* src, int64_t ld, int64_t rows, int64_t cols,
+                                           void* planes, void* stream);
 
 B2CTR_API size_t b2ctr_gemm_workspace_bytes(const b2ctr_gemm_t* g);
 B2CTR_API b2ctr_status_t b2ctr_gemm(const b2ctr_gemm_t* g, void* workspace, size_t workspace_bytes,

@@ -197,6 +197,32 @@ def test_gemm_bf16x3_tensor_core(cuda, m, n, k, ta, tb, variant):
     assert ((got - want).abs() <= bound).all(), float(((got - want).abs() / bound).max())
 
 
+@pytest.mark.parametrize("m,n,k", [(128, 128, 64), (257, 256, 845), (4096, 256, 848), (300, 40, 200), (1000, 1, 64),
+                                   (845, 256, 4100), (4096, 845, 256), (515, 384, 130)])
+@pytest.mark.parametrize("ta,tb", [(False, False), (False, True), (True, False), (True, True)])
+@pytest.mark.parametrize("given", ["a", "b", "ab"])
+def test_gemm_bf16x3_with_caller_planes(cuda, m, n, k, ta, tb, given):
+    """b2ctr_split_planes output handed to b2ctr_gemm (a_planes / b_planes) must give the same result as
+    the GEMM splitting its operands itself: the planes are a pure function of the stored matrix."""
+    K, L = _kern()
+    rng = np.random.RandomState(m + 3 * n + k)
+    a = _r(rng, *((k, m) if ta else (m, k))).to(cuda)
+    b = _r(rng, *((n, k) if tb else (k, n))).to(cuda)
+    ap = K.split_planes(a) if "a" in given else None
+    bp = K.split_planes(b) if "b" in given else None
+    sk = 4 if k > 2048 else 1
+    want = K.gemm(a, b, trans_a=ta, trans_b=tb, precision=L.GEMM_BF16X3, m=m, n=n, k=k, split_k=sk, variant=3)
+    got = K.gemm(a, b, trans_a=ta, trans_b=tb, precision=L.GEMM_BF16X3, m=m, n=n, k=k, split_k=sk, variant=3,
+                 a_planes=ap, b_planes=bp)
+    assert torch.equal(want, got)
+    # strided source (leading window of a wider buffer), as ops.dense passes the embedding concat buffer
+    wide = torch.zeros((a.shape[0], a.shape[1] + 5), device=cuda)
+    wide[:, :a.shape[1]] = a
+    got2 = K.gemm(wide[:, :a.shape[1]], b, trans_a=ta, trans_b=tb, precision=L.GEMM_BF16X3, m=m, n=n, k=k,
+                  split_k=sk, variant=3, a_planes=K.split_planes(wide[:, :a.shape[1]]), b_planes=bp)
+    assert torch.equal(want, got2)
+
+
 @pytest.mark.parametrize("variant", [1, 2, 3])
 def test_gemm_bf16x3_splitk_accumulate(cuda, variant):
     K, L = _kern()

@@ -29,7 +29,7 @@ def test_struct_layouts_match_header():
     from deepctr_b200 import _lib as L
     assert ctypes.sizeof(L.Feature) == 112
     assert L.Feature.src_table.offset == 96
-    assert ctypes.sizeof(L.Gemm) == 112
+    assert ctypes.sizeof(L.Gemm) == 128
     assert ctypes.sizeof(L.UniformGather) == 104
 
 

@@ -647,6 +647,11 @@ static cudaError_t launch_planes(const PlaneArgs& pa, cudaStream_t st) {
 }
 
 static inline int64_t round_up(int64_t v, int64_t q) { return (v + q - 1) / q * q; }
+// Padded extent of caller planes: rows to 256 (largest N tile of a K-major B / M tile pair), columns to 128
+// (M tile of an MN-major A, N tiles of an MN-major B); narrow matrices (<= 64 columns) pad to one 64-wide
+// swizzle atom only - a 128-wide MN-major tile then runs into the next plane row, which only feeds output
+// rows/columns >= m/n that are never stored.
+static inline int64_t planes_cols_pad(int64_t cols) { return cols <= 64 ? 64 : round_up(cols, 128); }
 static inline int planes_bn(int64_t n, int64_t k) {
   if (n <= 32) return 32;
   if (n <= 64) return 64;
@@ -695,7 +700,7 @@ static b2ctr_status_t gemm_planes(const b2ctr_gemm_t* g, void* workspace, size_t
   const int64_t b_sr = g->trans_b ? g->n : g->k, b_sc = g->trans_b ? g->k : g->n;
   const bool a_given = g->a_planes && (a_kc || mn_ok);
   bool b_given = g->b_planes && (b_kc || (mn_ok && bn >= 64));
-  if (b_given && !b_kc && round_up(b_sc, 128) % bn != 0) bn = 128;   // MN-major tiles must stay inside the pad
+  if (b_given && !b_kc && planes_cols_pad(b_sc) % bn != 0) bn = planes_cols_pad(b_sc) == 64 ? 64 : 128;   // N tiles inside the pad
   const int64_t np = round_up(g->n, bn);
   const int a_mn = a_given ? !a_kc : ((!a_kc && mn_ok) ? 1 : 0);
   const int b_mn = b_given ? !b_kc : ((!b_kc && mn_ok && bn >= 64) ? 1 : 0);   // an MN atom is 64 elements wide
@@ -713,7 +718,7 @@ static b2ctr_status_t gemm_planes(const b2ctr_gemm_t* g, void* workspace, size_t
     split_planes_t_kernel<<<grid, 256, 0, st>>>(p, ld, rows, g->k, rows_pad, kp, hi, lo);
   };
   if (a_given) {
-    const int64_t rp = round_up(a_sr, 256), cp = round_up(a_sc, 128);
+    const int64_t rp = round_up(a_sr, 256), cp = planes_cols_pad(a_sc);
     a_hi = (__nv_bfloat16*)g->a_planes; a_lo = a_hi + rp * cp; a_pitch = cp;
   } else {
     a_hi = (__nv_bfloat16*)w; a_lo = a_hi + mp * kp; w = (unsigned char*)(a_lo + mp * kp);
@@ -724,7 +729,7 @@ static b2ctr_status_t gemm_planes(const b2ctr_gemm_t* g, void* workspace, size_t
     B2_CHECK_LAUNCH("b2ctr_gemm(bf16x3 split A)");
   }
   if (b_given) {
-    const int64_t rp = round_up(b_sr, 256), cp = round_up(b_sc, 128);
+    const int64_t rp = round_up(b_sr, 256), cp = planes_cols_pad(b_sc);
     b_hi = (__nv_bfloat16*)g->b_planes; b_lo = b_hi + rp * cp; b_pitch = cp;
   } else {
     b_hi = (__nv_bfloat16*)w; b_lo = b_hi + np * kp;
@@ -764,11 +769,11 @@ static b2ctr_status_t gemm_planes(const b2ctr_gemm_t* g, void* workspace, size_t
 }
 
 size_t planes_bytes(int64_t rows, int64_t cols) {
-  return (size_t)round_up(rows, 256) * round_up(cols, 128) * 2 * sizeof(__nv_bfloat16);
+  return (size_t)round_up(rows, 256) * planes_cols_pad(cols) * 2 * sizeof(__nv_bfloat16) + 256;
 }
 b2ctr_status_t split_planes(const float* src, int64_t ld, int64_t rows, int64_t cols, void* planes,
                             cudaStream_t st) {
-  const int64_t rp = round_up(rows, 256), cp = round_up(cols, 128);
+  const int64_t rp = round_up(rows, 256), cp = planes_cols_pad(cols);
   __nv_bfloat16* hi = (__nv_bfloat16*)planes;
   const int vec = (ld % 4 == 0) && (((uintptr_t)src & 15) == 0);
   split_planes_kernel<<<grid_for(rp * (cp / 8), 256, 8), 256, 0, st>>>(src, ld, rows, cols, rp, cp, hi, hi + rp * cp,

@@ -18,6 +18,8 @@ import inspect
 import threading
 from collections import OrderedDict
 
+import os
+
 import numpy as np
 import torch
 
@@ -913,7 +915,7 @@ class Model(object):
 
     # ---- execution ---------------------------------------------------------------------------
     def compile(self, optimizer="adam", loss=None, metrics=None, embedding_update="auto", distributed="auto",
-                **kw):
+                step_graph="auto", **kw):
         """``embedding_update``: 'dense' = Keras semantics (dense gradient + dense optimizer + l2 on
         the whole table; O(vocab) per step), 'sparse' = fused row-wise SGD scatter
         (O(batch); l2 on tables must be 0), 'auto' = dense below 4M table elements."""
@@ -924,6 +926,12 @@ class Model(object):
         if embedding_update not in ("auto", "dense", "sparse"):
             raise ValueError("embedding_update must be auto / dense / sparse")
         self.planner.configure(self.optimizer, embedding_update)
+        # CUDA-graph replay of the training step ('auto': on whenever the step is capturable)
+        from . import ops as _ops
+        self.step_graph = step_graph if os.environ.get("B2CTR_STEP_GRAPH", "1") != "0" else "off"
+        self._step_graphs, self._graph_pool, self._eager_steps = {}, None, 0
+        self.replayed_launches = 0             # kernels executed through graph replays (bench accounting)
+        self._uncapturable0 = _ops.UNCAPTURABLE
         # multi-GPU (one process per GPU): dense weights data-parallel, fast-path tables row-sharded
         self.dist = None
         if distributed not in (None, False):
@@ -995,34 +1003,97 @@ class Model(object):
         return contiguous(vals[id(out)]).reshape(-1, 1)
 
     def _stage_batch(self, x, y, stream=None):
-        """Pack + H2D one batch (optionally on a side stream); returns (feed, labels, ready event)."""
+        """Pack + H2D one batch (optionally on a side stream); returns (feed, labels, ready event, slot)."""
         if stream is None:
-            return self._feed(x), self._feeder.labels(y), None
+            feed = self._feed(x)
+            return feed, self._feeder.labels(y), None, self._feeder.slot
         with torch.cuda.stream(stream):
             feed = self._feed(x)
             labels = self._feeder.labels(y)
             ev = torch.cuda.Event()
             ev.record(stream)
-        return feed, labels, ev
+        return feed, labels, ev, self._feeder.slot
 
     def _loss_step(self, x, y, train, staged=None):
-        """forward (+ backward + update when ``train``); returns the device loss_sum tensor [1] and
-        batch size - no host synchronisation here."""
+        """forward (+ backward + update when ``train``); returns the device loss_sum tensor [1], the
+        predictions and the batch size - no host synchronisation here.
+
+        Training steps are replayed as CUDA graphs once warm: the whole step (fused gather, GEMMs, loss,
+        backward, scatter/optimizer kernels) is captured per staging-ring slot, so a step costs one
+        cudaGraphLaunch on the host instead of ~70 kernel launches."""
         if self.optimizer is None:
             raise RuntimeError("You must compile your model before training/testing.")
         self._materialize()
         if staged is None:
-            feed = self._feed(x)
-            labels = self._feeder.labels(y)
-        else:
-            feed, labels, ev = staged
-            if ev is not None:
-                cur = torch.cuda.current_stream()
-                cur.wait_event(ev)
-                for v in list(feed.values()) + [E_labels(labels)]:   # staged on a side stream: tell the allocator
-                    t = v.data if isinstance(v, Var) else v
-                    if t is not None and t.is_cuda:
-                        t.record_stream(cur)
+            staged = self._stage_batch(x, y)
+        feed, labels, ev, slot = staged
+        if ev is not None:
+            torch.cuda.current_stream().wait_event(ev)
+        try:
+            if train and self._graph_eligible():
+                key = self._graph_key(feed, labels)
+                ent = self._step_graphs.get(key)
+                if ent is None and self._eager_steps >= 2 and len(self._step_graphs) < 8:
+                    ent = self._capture_step(key, feed, labels)
+                if ent is not None:
+                    self.optimizer.iterations += 1
+                    ent[0].replay()
+                    self.replayed_launches += ent[4]
+                    return ent[1], ent[2], ent[3]
+            out = self._loss_step_impl(feed, labels, train)
+            if train:
+                self._eager_steps += 1
+            return out
+        finally:
+            self._feeder.consumed(slot)
+
+    # ---- CUDA-graph replay of the training step ---------------------------------------------------
+    def _graph_eligible(self):
+        from . import ops
+        if self.step_graph in (False, None, "off") or K.PROFILE is not None or getattr(self, "dist", None) is not None:
+            return False
+        if self.optimizer.name == "adam":      # step-dependent bias correction is a by-value kernel argument
+            return False
+        return ops.UNCAPTURABLE == self._uncapturable0
+
+    def _graph_key(self, feed, labels):
+        items = []
+        for name in sorted(feed):
+            v = feed[name]
+            t = v.data if isinstance(v, Var) else v
+            if t is not None:
+                items.append((name, t.data_ptr(), tuple(t.shape), tuple(t.stride()), str(t.dtype)))
+        return (tuple(items), labels.data_ptr(), tuple(labels.shape), float(self.optimizer.lr),
+                torch.cuda.current_device())
+
+    def _capture_step(self, key, feed, labels):
+        from . import ops
+        it0 = self.optimizer.iterations
+        n0 = L.launch_count()
+        graph = torch.cuda.CUDAGraph()
+        try:
+            with torch.cuda.graph(graph, pool=self._graph_pool, capture_error_mode="thread_local"):
+                loss_sum, pred, batch = self._loss_step_impl(feed, labels, True)
+        except Exception as exc:               # something on this model's path cannot be captured: stay eager
+            import warnings
+            warnings.warn("step graph capture failed (%s: %s); training continues with eager launches"
+                          % (type(exc).__name__, exc))
+            self.step_graph = "off"
+            self.optimizer.iterations = it0
+            for w in self.weights:             # nothing ran on the device; drop the half-built python state
+                w.grad = None
+            return None
+        self.optimizer.iterations = it0        # capturing does not execute the step
+        if ops.UNCAPTURABLE != self._uncapturable0:
+            self.step_graph = "off"
+            return None
+        if self._graph_pool is None:
+            self._graph_pool = graph.pool()
+        ent = (graph, loss_sum, pred, batch, L.launch_count() - n0)
+        self._step_graphs[key] = ent
+        return ent
+
+    def _loss_step_impl(self, feed, labels, train):
         logit_t, head = self._head()
         if head is None:
             raise ValueError("training needs a PredictionLayer output (all builders end with one)")
@@ -1038,7 +1109,6 @@ class Model(object):
             bias = player.global_bias.materialize() if player.use_bias else None
             pred, dlogit, dbias, loss_sum = K.predict_loss(lt, bias, labels, task, want_grad=train)
         if train:
-            batch = lt.shape[0]
             logit.requires_grad = True
             add_grad(logit, dlogit.reshape(logit.data.shape))
             if bias is not None:
@@ -1154,6 +1224,8 @@ class Model(object):
                 staged = fut.result()
                 fut = self._stage_pool.submit(stage, starts[i + 1]) if i + 1 < len(starts) else None
                 ls, _, b = self._loss_step(None, None, True, staged=staged)
+                # (graph replay: `ls` is the graph's static output; the copy below is stream-ordered before
+                # the next replay overwrites it)
                 host_losses[i:i + 1].copy_(ls, non_blocking=True)
                 cnt += b
             torch.cuda.synchronize()

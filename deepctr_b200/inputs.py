@@ -734,6 +734,8 @@ class Feeder(object):
             if s.hash[1] is not None:
                 self.host_hash[s.input_name] = s.hash[1]
         self._pinned = {}
+        self._copied_ev = {}
+        self._consumed_ev = {}
         self.h2d_bytes = 0
 
     def _as_dict(self, x):
@@ -749,36 +751,55 @@ class Feeder(object):
 
     _RING = 3
 
-    def _stage(self, key, shape, dtype):
-        """Pinned staging buffer from a small ring: a slot is reused only after the H2D copy that last
-        read it has completed (the host may run several steps ahead of the GPU)."""
-        ring = self._pinned.setdefault(key, {"slot": 0, "bufs": [None] * self._RING,
-                                             "events": [None] * self._RING})
-        i = ring["slot"] = (ring["slot"] + 1) % self._RING
-        n = int(np.prod(shape))
-        if ring["events"][i] is not None:
-            ring["events"][i].synchronize()
-        buf = ring["bufs"][i]
-        if buf is None or buf.numel() < n:
-            buf = torch.empty(max(n, 1), dtype=dtype)
-            try:
-                buf = buf.pin_memory()
-            except Exception:
-                pass
-            ring["bufs"][i] = buf
-        self._last_stage = (ring, i)
-        return buf[:n].reshape(shape)
+    # Staging ring.  One feed() + labels() pair uses ONE slot: a pinned host buffer and a persistent device
+    # buffer per dtype group.  Persistent device addresses are what lets the training step be replayed as a
+    # CUDA graph (engine.Model._loss_step keys its graphs on them).  Two guards per slot:
+    #   copied[slot]   - recorded after the H2D copies; the host waits on it before overwriting the pinned side
+    #   consumed[slot] - recorded by the model on the compute stream after the step that read the device side;
+    #                    the staging stream waits on it before the next H2D into that slot
+    def _next_slot(self):
+        self.slot = (getattr(self, "slot", -1) + 1) % self._RING
+        ev = self._copied_ev.get(self.slot)
+        if ev is not None:
+            ev.synchronize()
+        ev = self._consumed_ev.get(self.slot)
+        if ev is not None:
+            torch.cuda.current_stream().wait_event(ev)
+        return self.slot
 
-    def _copied(self):
-        ring, i = self._last_stage
-        ev = ring["events"][i]
+    def consumed(self, slot):
+        """The kernels reading slot `slot` have been enqueued on the current stream."""
+        ev = self._consumed_ev.get(slot)
         if ev is None:
-            ev = ring["events"][i] = torch.cuda.Event()
+            ev = self._consumed_ev[slot] = torch.cuda.Event()
         ev.record()
 
+    def _stage(self, key, shape, dtype):
+        """(pinned host view, device view) of the current slot for dtype group `key`."""
+        n = int(np.prod(shape))
+        bufs = self._pinned.setdefault((key, self.slot), [None, None])
+        if bufs[0] is None or bufs[0].numel() < n:
+            host = torch.empty(max(n, 1), dtype=dtype)
+            try:
+                host = host.pin_memory()
+            except Exception:
+                pass
+            bufs[0] = host
+            bufs[1] = torch.empty(max(n, 1), dtype=dtype, device=E.device())
+        return bufs[0][:n].reshape(shape), bufs[1][:n].reshape(shape)
+
+    def _upload(self, host, dev):
+        dev.copy_(host, non_blocking=True)
+        ev = self._copied_ev.get(self.slot)
+        if ev is None:
+            ev = self._copied_ev[self.slot] = torch.cuda.Event()
+        ev.record()
+        self.h2d_bytes += host.numel() * host.element_size()
+        return dev
+
     def feed(self, x, batch_slice=None):
-        dev = E.device()
         xd = self._as_dict(x)
+        self._next_slot()
         groups = {"i32": [], "i64": [], "f32": []}
         arrays = {}
         for name in self.names:
@@ -816,15 +837,13 @@ class Feeder(object):
             if key != "f32":
                 # ids: one flat staging buffer of per-input contiguous blocks (a plain memcpy per input on
                 # the host, one H2D for all); the gather kernels take a pointer + stride per feature
-                stage = self._stage(key, (b * total,), th_dt[key])
+                stage, dbuf = self._stage(key, (b * total,), th_dt[key])
                 sn = stage.numpy()
                 off = 0
                 for name, a, w in items:
                     sn[off:off + b * w].reshape(b, w)[...] = a
                     off += b * w
-                pack = stage.to(dev, non_blocking=True)
-                self._copied()
-                self.h2d_bytes += stage.numel() * stage.element_size()
+                pack = self._upload(stage, dbuf)
                 off = 0
                 for name, a, w in items:
                     spec = self.specs[name]
@@ -836,18 +855,20 @@ class Feeder(object):
                 continue
             # floats: contiguous per-input blocks on the host (plain memcpy), one H2D, then a device kernel
             # builds the row-major [B, total] dense pack (a strided host-side pack costs ~2 ms at B = 65536)
-            stage = self._stage(key, (b * total,), th_dt[key])
+            stage, dbuf = self._stage(key, (b * total,), th_dt[key])
             sn = stage.numpy()
             off = 0
             for name, a, w in items:
                 sn[off:off + b * w].reshape(b, w)[...] = a
                 off += b * w
-            flat = stage.to(dev, non_blocking=True)
-            self._copied()
-            self.h2d_bytes += stage.numel() * stage.element_size()
+            flat = self._upload(stage, dbuf)
             if len(items) > 64:
                 raise ValueError("more than 64 dense inputs are not supported")
-            pack = K.pack_rows(flat, [w for _, _, w in items], b) if len(items) > 1 else flat.reshape(b, total)
+            if len(items) > 1:
+                _, pbuf = self._stage("f32pack", (b, total), torch.float32)
+                pack = K.pack_rows(flat, [w for _, _, w in items], b, out=pbuf)
+            else:
+                pack = flat.reshape(b, total)
             base = E.Var(pack, name="__dense_pack__" if key == "f32" else "__id_pack_%s__" % key)
             if key == "f32":
                 feed["__dense_pack__"] = base
@@ -895,12 +916,11 @@ class Feeder(object):
         if isinstance(y, torch.Tensor) and y.is_cuda:
             return y.reshape(-1).float()
         a = np.asarray(y, dtype=np.float32).reshape(-1)
-        stage = self._stage("labels", (a.shape[0],), torch.float32)
+        if not hasattr(self, "slot"):
+            self._next_slot()
+        stage, dbuf = self._stage("labels", (a.shape[0],), torch.float32)
         stage.numpy()[:] = a
-        self.h2d_bytes += a.nbytes
-        out = stage.to(E.device(), non_blocking=True)
-        self._copied()
-        return out
+        return self._upload(stage, dbuf)
 
 
 def _dense_strides(shape):

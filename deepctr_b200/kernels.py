@@ -11,6 +11,7 @@ import torch
 from . import _lib as L
 
 _workspace = {}
+_retired = []
 
 
 def _require_cuda(*tensors):
@@ -34,7 +35,12 @@ def workspace(nbytes, device):
     key = (device.index if device.index is not None else torch.cuda.current_device())
     buf = _workspace.get(key)
     if buf is None or buf.numel() < nbytes:
-        buf = torch.empty(max(nbytes, 1 << 20), dtype=torch.uint8, device=device)
+        if buf is not None:
+            _retired.append(buf)      # captured step graphs may still reference the old scratch: keep it
+        size = max(nbytes, 1 << 20, 2 * buf.numel() if buf is not None else 0)
+        if torch.cuda.is_current_stream_capturing():
+            raise RuntimeError("workspace growth during CUDA-graph capture (run the step eagerly first)")
+        buf = torch.empty(size, dtype=torch.uint8, device=device)
         _workspace[key] = buf
     return buf
 
@@ -252,11 +258,12 @@ def copy2d(src, ld_src, dst, ld_dst, rows, cols, accumulate=False, src_off=0, ds
     return dst
 
 
-def pack_rows(src_flat, widths, batch):
+def pack_rows(src_flat, widths, batch, out=None):
     """[sum_i B*w_i] flat blocks -> row-major [B, sum w_i]."""
     _require_cuda(src_flat)
     total = int(sum(widths))
-    out = torch.empty((batch, total), dtype=torch.float32, device=src_flat.device)
+    if out is None:
+        out = torch.empty((batch, total), dtype=torch.float32, device=src_flat.device)
     arr = (C.c_int32 * len(widths))(*[int(w) for w in widths])
     L.check(L.lib().b2ctr_pack_rows(ptr(src_flat), arr, len(widths), batch, ptr(out), total, stream()), "pack_rows")
     return out

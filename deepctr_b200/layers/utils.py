@@ -157,6 +157,8 @@ class Hash(Layer):
 
     def call(self, x, mask=None, **kwargs):
         if self.vocabulary_path:
+            from .. import ops
+            ops.mark_uncapturable()           # host-side vocabulary lookup: not CUDA-graph capturable
             ids = x.data.cpu().numpy()
             out = host_hash_array(ids, self.num_buckets, self.mask_zero, self.vocabulary_path, self.default_value)
             return E.Var(torch.from_numpy(out).to(x.data.device))

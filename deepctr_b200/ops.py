@@ -17,6 +17,16 @@ GEMM_PRECISION = L.GEMM_FP32
 PLANE_REUSE = True
 
 
+# bumped by ops whose kernels take per-step by-value state (dropout seeds) or that need the host (string
+# hashing): a model that ran one of them is never replayed as a CUDA graph (engine.Model._graph_eligible)
+UNCAPTURABLE = 0
+
+
+def mark_uncapturable():
+    global UNCAPTURABLE
+    UNCAPTURABLE += 1
+
+
 def set_gemm_precision(mode):
     """'fp32' (exact FFMA) or 'bf16x3' (tcgen05 split-bf16, ~2^-17 relative)."""
     global GEMM_PRECISION
@@ -65,11 +75,12 @@ def dense(x, w, b=None, activation=None):
     wd = w.materialize() if isinstance(w, E.Weight) else w.data
     bd = (b.materialize() if isinstance(b, E.Weight) else b.data) if b is not None else None
     # BF16X3: operands are split into bf16 planes once and the planes are reused by forward/dgrad/wgrad
-    reuse = GEMM_PRECISION == L.GEMM_BF16X3 and PLANE_REUSE and m >= 128
+    # skinny layers (the final [*, 1] projection) are GEMVs: exact-fp32 FFMA path, no tensor-core staging
+    prec = GEMM_PRECISION if min(n, kdim) >= 16 else L.GEMM_FP32
+    reuse = prec == L.GEMM_BF16X3 and PLANE_REUSE and m >= 128
     xp = _planes_of(x, x2) if reuse else None
     wp = K.split_planes(wd) if reuse else None
-    y = K.gemm(x2, wd, bias=bd, act=fused_act, precision=GEMM_PRECISION, m=m, n=n, k=kdim, a_planes=xp,
-               b_planes=wp)
+    y = K.gemm(x2, wd, bias=bd, act=fused_act, precision=prec, m=m, n=n, k=kdim, a_planes=xp, b_planes=wp)
     out = E.Var(y.reshape(tuple(x.data.shape[:-1]) + (n,)))
     if act is None and activation is not None:
         raise ValueError("activation %r cannot be fused into dense(); apply it as a layer" % activation)
@@ -95,15 +106,15 @@ def dense(x, w, b=None, activation=None):
                 ld = base.data.stride(0)
                 buf = _empty((m, ld), dy)
                 dxw = buf[:, :kdim]
-                K.gemm(dz, wd, c=dxw, trans_b=True, precision=GEMM_PRECISION, m=m, n=kdim, k=n, a_planes=dzp,
+                K.gemm(dz, wd, c=dxw, trans_b=True, precision=prec, m=m, n=kdim, k=n, a_planes=dzp,
                        b_planes=wp)
                 E.add_grad(x, dxw)
             else:
-                dx = K.gemm(dz, wd, trans_b=True, precision=GEMM_PRECISION, m=m, n=kdim, k=n, a_planes=dzp,
+                dx = K.gemm(dz, wd, trans_b=True, precision=prec, m=m, n=kdim, k=n, a_planes=dzp,
                             b_planes=wp)
                 E.add_grad(x, dx.reshape(x.data.shape))
         if w.requires_grad:
-            dw = K.gemm(x2, dz, trans_a=True, precision=GEMM_PRECISION, split_k=_split_k(kdim, n, m),
+            dw = K.gemm(x2, dz, trans_a=True, precision=prec, split_k=_split_k(kdim, n, m),
                         m=kdim, n=n, k=m, a_planes=xp, b_planes=dzp)
             E.add_grad(w, dw)
         if need_db:
@@ -755,6 +766,7 @@ def batchnorm(x, gamma, beta, moving_mean, moving_var, eps, training, momentum=0
 
 
 def dropout(x, rate, seed):
+    mark_uncapturable()
     xt = E.contiguous(x)
     res = E.Var(K.dropout(xt, rate, seed))
 

@@ -187,7 +187,8 @@ typedef struct b2ctr_gemm {
 } b2ctr_gemm_t;
 
 /* bf16 (hi, lo) planes of an fp32 matrix [rows, cols]: hi = bf16(x), lo = bf16(x - hi), zero padded to
- * [round_up(rows,256), round_up(cols,128)]; the buffer holds the hi plane followed by the lo plane. */
+ * [round_up(rows,256), cols <= 64 ? 64 : round_up(cols,128)]; the buffer holds the hi plane followed by the
+ * lo plane (b2ctr_planes_bytes() includes the slack the tile loads need). */
 B2CTR_API size_t b2ctr_planes_bytes(int64_t rows, int64_t cols);
 B2CTR_API b2ctr_status_t b2ctr_split_planes(const float* src, int64_t ld, int64_t rows, int64_t cols,
                                            void* planes, void* stream);

@@ -101,3 +101,40 @@ def test_save_and_load_weights_roundtrip(cuda, tmp_path):
     model.load_weights(p)
     # the second predict runs the fused FM / linear epilogues (different fp32 summation order)
     np.testing.assert_allclose(a, model.predict(x, batch_size=256), rtol=1e-5, atol=1e-6)
+
+
+def test_training_step_graph_replay_matches_eager(cuda):
+    """After two eager steps the whole training step is captured per staging-ring slot and replayed as a CUDA
+    graph (engine.Model._loss_step).  Same kernels, same order: the losses must agree with a model that keeps
+    launching eagerly, up to the order of the fp32 atomics in the embedding scatter."""
+    import numpy as np
+    from deepctr_b200.models import DeepFM
+    from deepctr_b200.engine import SGD
+    from deepctr_b200.feature_column import SparseFeat, DenseFeat, VarLenSparseFeat
+    cols = [SparseFeat("C%d" % i, 50 + i, 8) for i in range(5)] + [DenseFeat("I%d" % i, 1) for i in range(3)] + \
+           [VarLenSparseFeat(SparseFeat("V", 30, 8), maxlen=4, combiner="mean")]
+    rng = np.random.RandomState(3)
+    n, bs = 96 * 9, 96
+    x = {"C%d" % i: rng.randint(0, 50 + i, n).astype(np.int32) for i in range(5)}
+    x.update({"I%d" % i: rng.rand(n).astype(np.float32) for i in range(3)})
+    x["V"] = rng.randint(0, 30, (n, 4)).astype(np.int32)
+    y = rng.randint(0, 2, n).astype(np.float32)
+    losses = {}
+    for mode in ("off", "auto"):
+        m = DeepFM(cols, cols, dnn_hidden_units=(16, 8), seed=7)
+        m.compile(SGD(0.05), "binary_crossentropy", step_graph=mode)
+        h = m.fit(x, y, batch_size=bs, epochs=3, shuffle=False, verbose=0)
+        per_batch = [m.test_on_batch({k: v[:bs] for k, v in x.items()}, y[:bs])]
+        losses[mode] = (h.history["loss"], per_batch, m)
+    m = losses["auto"][2]
+    assert len(m._step_graphs) == 3 and m.replayed_launches > 0      # one graph per staging-ring slot
+    assert not losses["off"][2]._step_graphs
+    np.testing.assert_allclose(losses["auto"][0], losses["off"][0], rtol=2e-5)
+    np.testing.assert_allclose(losses["auto"][1], losses["off"][1], rtol=2e-5)
+    for wa, wo in zip(m.weights, losses["off"][2].weights):
+        np.testing.assert_allclose(wa.value(), wo.value(), rtol=1e-4, atol=1e-6)
+    # a model with dropout keeps launching eagerly (the Philox offset is a by-value kernel argument)
+    md = DeepFM(cols, cols, dnn_hidden_units=(16, 8), dnn_dropout=0.5, seed=7)
+    md.compile(SGD(0.05), "binary_crossentropy")
+    md.fit(x, y, batch_size=bs, epochs=1, shuffle=False, verbose=0)
+    assert not md._step_graphs

@@ -646,6 +646,393 @@ static cudaError_t launch_planes(const PlaneArgs& pa, cudaStream_t st) {
   return cudaGetLastError();
 }
 
+
+// ================================================================================================
+// Variant 4: persistent, warp-specialised, optionally CTA-PAIRED (tcgen05 cta_group::2) planes GEMM.
+//
+// The split-bf16 scheme moves 2x the operand bytes of a plain bf16 GEMM for 3x its MMAs, so operand
+// delivery (L2 -> shared memory), not the tensor pipe, is what a 128x256 single-CTA tile runs out of
+// (96 KB per 64-deep k-block per SM, ~11 TB/s over 148 SMs).  A CTA pair computes a 256 x BN tile with
+// each CTA staging its own 128 rows of A and only HALF of the B tile (the pair's tensor cores read both
+// halves), i.e. 64 KB per k-block per SM at BN = 256 - which also leaves room for a 3-deep pipeline.
+//   warps 0-3 : epilogue (TMEM -> registers -> global), one TMEM sub-partition each
+//   warps 4-7 : producers (cp.async 16 B chunks into the SWIZZLE_128B stage layout)
+//   warp  8   : TMEM allocation; lane 0 of the LEADER CTA issues every tcgen05.mma of the pair
+// TMEM holds two BN-column accumulators: the epilogue of tile i overlaps the main loop of tile i+1.
+// Persistent: grid = min(#tiles, #SMs / NCTA) clusters; tile = cluster id + j * #clusters, N-tile fastest
+// (neighbouring clusters share the A rows through L2).
+// ================================================================================================
+constexpr int kWsThreads = 9 * 32;
+constexpr int kWsProducers = 4;   // warps
+
+struct WsArgs {
+  PlaneArgs p;
+  int tiles_m, tiles_n;   // cluster tiles
+  int64_t ntiles;
+};
+
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+// arrive on the barrier at the same shared-memory offset in CTA `cta` of the cluster
+__device__ __forceinline__ void mbar_arrive_cluster(uint64_t* bar, uint32_t cta) {
+  asm volatile(
+      "{\n\t"
+      ".reg .b32 ra;\n\t"
+      "mapa.shared::cluster.u32 ra, %0, %1;\n\t"
+      "mbarrier.arrive.release.cluster.shared::cluster.b64 _, [ra];\n\t"
+      "}\n" ::"r"(smem_u32(bar)),
+      "r"(cta)
+      : "memory");
+}
+__device__ __forceinline__ void mbar_wait_cluster(uint64_t* bar, uint32_t parity) {
+  uint32_t done;
+  do {
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t"
+        "}\n"
+        : "=r"(done)
+        : "r"(smem_u32(bar)), "r"(parity)
+        : "memory");
+  } while (!done);
+}
+template <int NCTA>
+__device__ __forceinline__ void umma_f16_ws(uint32_t tmem_d, uint64_t da, uint64_t db, uint32_t idesc,
+                                            uint32_t accumulate) {
+  if constexpr (NCTA == 1) {
+    umma_f16(tmem_d, da, db, idesc, accumulate);
+  } else {
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t"
+        "}\n" ::"r"(tmem_d),
+        "l"(da), "l"(db), "r"(idesc), "r"(accumulate)
+        : "memory");
+  }
+}
+template <int NCTA>
+__device__ __forceinline__ void umma_commit_ws(uint64_t* bar) {
+  if constexpr (NCTA == 1) {
+    umma_commit(bar);
+  } else {   // arrives on `bar` in BOTH CTAs of the pair once the MMAs issued so far have completed
+    asm volatile(
+        "tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(
+            smem_u32(bar)),
+        "h"((uint16_t)3)
+        : "memory");
+  }
+}
+
+template <int BN, int STAGES, int NCTA>
+__global__ void __launch_bounds__(kWsThreads, 1) gemm_planes_ws_kernel(const __grid_constant__ WsArgs w) {
+  const PlaneArgs& g = w.p;
+  constexpr int BNH = BN / NCTA;             // rows of the B tile staged by one CTA
+  constexpr int A_PLANE = kTM * 128;
+  constexpr int B_PLANE = BNH * 128;
+  constexpr int STAGE = 2 * A_PLANE + 2 * B_PLANE;
+  constexpr uint32_t TMEM_COLS = 2 * BN < 32 ? 32 : 2 * BN;
+  extern __shared__ unsigned char smem_raw[];
+  unsigned char* tiles = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) &
+                                                          ~(uintptr_t)1023);
+  __shared__ __align__(8) uint64_t full_bar[STAGES], empty_bar[STAGES], acc_full[2], acc_empty[2];
+  __shared__ uint32_t tmem_slot;
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t cta_rank = NCTA == 1 ? 0u : cluster_ctarank();
+  const int64_t cluster_id = blockIdx.x / NCTA, nclusters = gridDim.x / NCTA;
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < STAGES; ++s) {
+      mbar_init(&full_bar[s], kWsProducers * NCTA);   // used on the leader only
+      mbar_init(&empty_bar[s], 1);
+    }
+    for (int a = 0; a < 2; ++a) {
+      mbar_init(&acc_full[a], 1);
+      mbar_init(&acc_empty[a], 4 * NCTA);             // used on the leader only
+    }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 8) {
+    if constexpr (NCTA == 1) {
+      asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_slot)),
+                   "r"(TMEM_COLS)
+                   : "memory");
+      asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    } else {
+      asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_slot)),
+                   "r"(TMEM_COLS)
+                   : "memory");
+      asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+    }
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  if constexpr (NCTA > 1) cluster_sync_all();      // peer barriers initialised before any remote arrive
+  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+  const uint32_t tmem_base = tmem_slot;
+
+  // tile -> coordinates (N tile fastest, then M, then the split-K slice)
+  auto decode = [&](int64_t tile, int64_t& mt, int64_t& nt, int64_t& kbeg, int& nkb) {
+    nt = tile % w.tiles_n;
+    const int64_t rest = tile / w.tiles_n;
+    mt = rest % w.tiles_m;
+    const int64_t z = rest / w.tiles_m;
+    kbeg = z * g.k_per_split;
+    const int64_t kend = kbeg + g.k_per_split < g.k_pad ? kbeg + g.k_per_split : g.k_pad;
+    nkb = kend > kbeg ? (int)((kend - kbeg) / kTK) : 0;
+  };
+
+  if (warp >= 4 && warp < 4 + kWsProducers) {
+    // ------------------------------------------------------------------------------ producers
+    const int tid = threadIdx.x - 128;
+    constexpr int NT = kWsProducers * 32;
+    int64_t tile = cluster_id, mt = 0, nt = 0, kbeg = 0;
+    int nkb = 0, kb = 0;
+    while (tile < w.ntiles) {            // first tile with work
+      decode(tile, mt, nt, kbeg, nkb);
+      if (nkb > 0) break;
+      tile += nclusters;
+    }
+    uint32_t issued = 0, published = 0;
+    for (uint32_t it = 0; tile < w.ntiles || published < issued; ++it) {
+      if (tile < w.ntiles) {
+        const int s = it % STAGES;
+        mbar_wait(&empty_bar[s], ((it / STAGES) & 1) ^ 1);
+        const uint32_t st = smem_u32(tiles + (size_t)s * STAGE);
+        const int64_t k0 = kbeg + (int64_t)kb * kTK;
+        const int64_t m0 = (mt * NCTA + cta_rank) * kTM;
+        const int64_t n0 = nt * BN + (int64_t)cta_rank * BNH;
+#pragma unroll 4
+        for (int t = tid; t < kTM * 8; t += NT) {
+          uint32_t off;
+          int64_t src;
+          if (g.a_mn) {
+            const int kk = t / (kTM / 8), c = t % (kTM / 8);
+            off = (c >> 3) * 8192 + kk * 128 + (((c & 7) ^ (kk & 7)) << 4);
+            src = (k0 + kk) * g.a_pitch + m0 + c * 8;
+          } else {
+            const int r = t >> 3, c = t & 7;
+            off = r * 128 + ((c ^ (r & 7)) << 4);
+            src = (m0 + r) * g.a_pitch + k0 + c * 8;
+          }
+          cp_async16(st + off, g.a_hi + src);
+          cp_async16(st + A_PLANE + off, g.a_lo + src);
+        }
+#pragma unroll 4
+        for (int t = tid; t < BNH * 8; t += NT) {
+          uint32_t off;
+          int64_t src;
+          if (g.b_mn) {
+            const int kk = t / (BNH / 8), c = t % (BNH / 8);
+            off = (c >> 3) * 8192 + kk * 128 + (((c & 7) ^ (kk & 7)) << 4);
+            src = (k0 + kk) * g.b_pitch + n0 + c * 8;
+          } else {
+            const int r = t >> 3, c = t & 7;
+            off = r * 128 + ((c ^ (r & 7)) << 4);
+            src = (n0 + r) * g.b_pitch + k0 + c * 8;
+          }
+          cp_async16(st + 2 * A_PLANE + off, g.b_hi + src);
+          cp_async16(st + 2 * A_PLANE + B_PLANE + off, g.b_lo + src);
+        }
+        ++issued;
+        if (++kb == nkb) {               // next tile with work
+          kb = 0;
+          tile += nclusters;
+          while (tile < w.ntiles) {
+            decode(tile, mt, nt, kbeg, nkb);
+            if (nkb > 0) break;
+            tile += nclusters;
+          }
+        }
+      }
+      asm volatile("cp.async.commit_group;" ::: "memory");
+      if (it >= STAGES - 1 && published < issued) {
+        asm volatile("cp.async.wait_group %0;" ::"n"(STAGES - 1) : "memory");
+        asm volatile("fence.proxy.async;" ::: "memory");   // generic-proxy writes -> visible to the tensor core
+        __syncwarp();
+        if (lane == 0) mbar_arrive_cluster(&full_bar[published % STAGES], 0);
+        ++published;
+      }
+    }
+  } else if (warp == 8) {
+    // ------------------------------------------------------------------------------ MMA issuer
+    if (cta_rank == 0) {
+      const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(BN >> 3) << 17) |
+                             ((uint32_t)((kTM * NCTA) >> 4) << 24) | (g.a_mn ? (1u << 15) : 0u) |
+                             (g.b_mn ? (1u << 16) : 0u);
+      uint32_t it = 0, acc_it = 0;
+      for (int64_t tile = cluster_id; tile < w.ntiles; tile += nclusters) {
+        int64_t mt, nt, kbeg;
+        int nkb;
+        decode(tile, mt, nt, kbeg, nkb);
+        if (nkb == 0) continue;
+        const uint32_t ab = acc_it & 1;
+        mbar_wait_cluster(&acc_empty[ab], ((acc_it >> 1) & 1) ^ 1);
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        const uint32_t tmem_d = tmem_base + ab * BN;
+        for (int kb = 0; kb < nkb; ++kb, ++it) {
+          const int s = it % STAGES;
+          mbar_wait_cluster(&full_bar[s], (it / STAGES) & 1);
+          asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+          if (lane == 0) {
+            const uint32_t sa = smem_u32(tiles + (size_t)s * STAGE);
+            const uint32_t a_hi = sa, a_lo = sa + A_PLANE, b_hi = sa + 2 * A_PLANE, b_lo = sa + 2 * A_PLANE + B_PLANE;
+#pragma unroll
+            for (int ks = 0; ks < kTK / 16; ++ks) {
+              const uint64_t dah = umma_desc_any(a_hi, ks, g.a_mn), dal = umma_desc_any(a_lo, ks, g.a_mn);
+              const uint64_t dbh = umma_desc_any(b_hi, ks, g.b_mn), dbl = umma_desc_any(b_lo, ks, g.b_mn);
+              umma_f16_ws<NCTA>(tmem_d, dah, dbh, idesc, (kb | ks) ? 1u : 0u);
+              umma_f16_ws<NCTA>(tmem_d, dah, dbl, idesc, 1u);
+              umma_f16_ws<NCTA>(tmem_d, dal, dbh, idesc, 1u);
+            }
+            umma_commit_ws<NCTA>(&empty_bar[s]);
+            if (kb == nkb - 1) umma_commit_ws<NCTA>(&acc_full[ab]);
+          }
+          __syncwarp();
+        }
+        ++acc_it;
+      }
+    }
+  } else {
+    // ------------------------------------------------------------------------------ epilogue
+    const int sub = warp;   // warps 0-3 own TMEM lanes [32*warp, 32*warp + 32)
+    const bool vec_c = (g.ldc % 4 == 0) && ((reinterpret_cast<uintptr_t>(g.c) & 15) == 0) &&
+                       (!g.bias || (reinterpret_cast<uintptr_t>(g.bias) & 15) == 0);
+    const bool vec_ws = (g.n % 4 == 0);
+    uint32_t acc_it = 0;
+    for (int64_t tile = cluster_id; tile < w.ntiles; tile += nclusters) {
+      int64_t mt, nt, kbeg;
+      int nkb;
+      decode(tile, mt, nt, kbeg, nkb);
+      const int64_t z = tile / ((int64_t)w.tiles_n * w.tiles_m);
+      const uint32_t ab = acc_it & 1;
+      if (nkb > 0) {
+        mbar_wait(&acc_full[ab], (acc_it >> 1) & 1);
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+      }
+      const int64_t gm = (mt * NCTA + cta_rank) * kTM + sub * 32 + lane;
+#pragma unroll 1
+      for (int c0 = 0; c0 < BN; c0 += 32) {
+        const int64_t gn0 = nt * BN + c0;
+        if (gn0 >= g.n) break;           // warp-uniform
+        uint32_t r[32];
+        if (nkb > 0) {
+          const uint32_t taddr = tmem_base + ((uint32_t)(sub * 32) << 16) + ab * BN + (uint32_t)c0;
+          asm volatile(
+              "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+              "{%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,"
+              "%16,%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,%29,%30,%31}, [%32];\n"
+              : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]),
+                "=r"(r[7]), "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]),
+                "=r"(r[14]), "=r"(r[15]), "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]),
+                "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]),
+                "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+              : "r"(taddr));
+          asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+        } else {
+#pragma unroll
+          for (int j = 0; j < 32; ++j) r[j] = 0u;
+        }
+        if (gm < g.m) {
+          if (g.splits > 1) {
+            float* wrow = g.ws + (z * g.m + gm) * g.n + gn0;
+            if (vec_ws && gn0 + 32 <= g.n) {
+#pragma unroll
+              for (int j = 0; j < 32; j += 4)
+                *reinterpret_cast<float4*>(wrow + j) =
+                    make_float4(g.alpha * __uint_as_float(r[j]), g.alpha * __uint_as_float(r[j + 1]),
+                                g.alpha * __uint_as_float(r[j + 2]), g.alpha * __uint_as_float(r[j + 3]));
+            } else {
+#pragma unroll
+              for (int j = 0; j < 32; ++j)
+                if (gn0 + j < g.n) wrow[j] = g.alpha * __uint_as_float(r[j]);
+            }
+          } else if (vec_c && gn0 + 32 <= g.n) {
+            float* crow = g.c + gm * g.ldc + gn0;
+#pragma unroll
+            for (int j = 0; j < 32; j += 4) {
+              float4 v = make_float4(g.alpha * __uint_as_float(r[j]), g.alpha * __uint_as_float(r[j + 1]),
+                                     g.alpha * __uint_as_float(r[j + 2]), g.alpha * __uint_as_float(r[j + 3]));
+              if (g.accumulate) {
+                const float4 o = *reinterpret_cast<const float4*>(crow + j);
+                v.x += o.x; v.y += o.y; v.z += o.z; v.w += o.w;
+              }
+              if (g.bias) {
+                const float4 bb = __ldg(reinterpret_cast<const float4*>(g.bias + gn0 + j));
+                v.x += bb.x; v.y += bb.y; v.z += bb.z; v.w += bb.w;
+              }
+              v.x = act_apply(v.x, g.act); v.y = act_apply(v.y, g.act);
+              v.z = act_apply(v.z, g.act); v.w = act_apply(v.w, g.act);
+              *reinterpret_cast<float4*>(crow + j) = v;
+            }
+          } else {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) {
+              const int64_t gn = gn0 + j;
+              if (gn < g.n) {
+                float v = g.alpha * __uint_as_float(r[j]);
+                if (g.accumulate) v += g.c[gm * g.ldc + gn];
+                if (g.bias) v += g.bias[gn];
+                g.c[gm * g.ldc + gn] = act_apply(v, g.act);
+              }
+            }
+          }
+        }
+      }
+      if (nkb > 0) {      // hand the accumulator back to the MMA issuer of the pair
+        asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+        __syncwarp();
+        if (lane == 0) mbar_arrive_cluster(&acc_empty[ab], 0);
+        ++acc_it;
+      }
+    }
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  if constexpr (NCTA > 1) cluster_sync_all();      // no CTA leaves while its peer may still signal it
+  if (warp == 8) {
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    if constexpr (NCTA == 1)
+      asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(TMEM_COLS) : "memory");
+    else
+      asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(TMEM_COLS) : "memory");
+  }
+}
+
+template <int BN, int STAGES, int NCTA>
+static cudaError_t launch_ws(const WsArgs& wa, cudaStream_t st) {
+  constexpr size_t smem = (size_t)STAGES * (2 * kTM * 128 + 2 * (BN / NCTA) * 128) + 1024;
+  static_assert(smem <= 227 * 1024, "stage ring exceeds shared memory");
+  auto kern = gemm_planes_ws_kernel<BN, STAGES, NCTA>;
+  cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  if (e != cudaSuccess) return e;
+  const int64_t max_clusters = kNumSMs / NCTA;
+  const int64_t nclusters = wa.ntiles < max_clusters ? wa.ntiles : max_clusters;
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3((unsigned)(nclusters * NCTA));
+  cfg.blockDim = dim3(kWsThreads);
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = NCTA;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  return cudaLaunchKernelEx(&cfg, kern, wa);
+}
+
 static inline int64_t round_up(int64_t v, int64_t q) { return (v + q - 1) / q * q; }
 // Padded extent of caller planes: rows to 256 (largest N tile of a K-major B / M tile pair), columns to 128
 // (M tile of an MN-major A, N tiles of an MN-major B); narrow matrices (<= 64 columns) pad to one 64-wide
@@ -660,20 +1047,20 @@ static inline int planes_bn(int64_t n, int64_t k) {
 }
 
 static int tc_variant(const b2ctr_gemm_t* g) {
-  if (g->variant >= 1 && g->variant <= 3) return g->variant;
+  if (g->variant >= 1 && g->variant <= 4) return g->variant;
   static int mode = -1;
   if (mode < 0) {
     const char* ev = getenv("B2CTR_TC_VARIANT");
     mode = ev ? atoi(ev) : 3;
   }
-  return (mode >= 1 && mode <= 3) ? mode : 3;
+  return (mode >= 1 && mode <= 4) ? mode : 3;
 }
 
 size_t gemm_bf16x3_workspace_bytes(const b2ctr_gemm_t* g) {
   size_t splitk = g->split_k > 1 ? (size_t)g->split_k * g->m * g->n * sizeof(float) : 0;
   if (tc_variant(g) == 1) return splitk;
   const int bn = planes_bn(g->n, g->k / (g->split_k > 1 ? g->split_k : 1));
-  const int64_t kp = round_up(g->k > 0 ? g->k : 1, kTK), mp = round_up(g->m, kTM), np = round_up(g->n, 256);
+  const int64_t kp = round_up(g->k > 0 ? g->k : 1, kTK), mp = round_up(g->m, 2 * kTM), np = round_up(g->n, 256);
   return splitk + (size_t)(mp + np) * kp * 2 * sizeof(__nv_bfloat16) + 512;
 }
 
@@ -684,8 +1071,10 @@ static b2ctr_status_t gemm_planes(const b2ctr_gemm_t* g, void* workspace, size_t
     return B2CTR_ERR_WORKSPACE;
   }
   const int splits = g->split_k > 1 ? g->split_k : 1;
-  int bn = planes_bn(g->n, g->k / (g->split_k > 1 ? g->split_k : 1));
-  const int64_t kp = round_up(g->k > 0 ? g->k : 1, kTK), mp = round_up(g->m, kTM);
+  const bool ws_kernel = tc_variant(g) == 4;
+  int bn = ws_kernel ? (g->n <= 32 ? 32 : g->n <= 64 ? 64 : g->n <= 128 ? 128 : 256)
+                     : planes_bn(g->n, g->k / (g->split_k > 1 ? g->split_k : 1));
+  const int64_t kp = round_up(g->k > 0 ? g->k : 1, kTK), mp = round_up(g->m, 2 * kTM);
   unsigned char* w = (unsigned char*)workspace;
   float* ws = (float*)w;
   w += splits > 1 ? (size_t)splits * g->m * g->n * sizeof(float) : 0;
@@ -694,7 +1083,7 @@ static b2ctr_status_t gemm_planes(const b2ctr_gemm_t* g, void* workspace, size_t
   // variant 3: row-contiguous sources keep their layout (MN-major planes) and the UMMA descriptors do the
   // transposition - the same planes then serve every GEMM that reads the tensor (forward / dgrad / wgrad),
   // which is what caller-provided planes (g->a_planes / g->b_planes) exploit.
-  const bool mn_ok = tc_variant(g) == 3;
+  const bool mn_ok = tc_variant(g) >= 3;
   const bool a_kc = !g->trans_a, b_kc = g->trans_b != 0;
   const int64_t a_sr = g->trans_a ? g->k : g->m, a_sc = g->trans_a ? g->m : g->k;   // stored rows / cols
   const int64_t b_sr = g->trans_b ? g->n : g->k, b_sc = g->trans_b ? g->k : g->n;
@@ -749,7 +1138,26 @@ static b2ctr_status_t gemm_planes(const b2ctr_gemm_t* g, void* workspace, size_t
   pa.alpha = g->alpha; pa.act = g->act; pa.accumulate = g->accumulate; pa.splits = splits;
   cudaError_t e;
   const bool short_k = pa.k_per_split <= 4 * kTK;
-  if (bn == 32) e = short_k ? launch_planes<32, 1>(pa, st) : launch_planes<32, 4>(pa, st);
+  if (ws_kernel) {
+    WsArgs wa;
+    wa.p = pa;
+    int ncta = g->m > kTM ? 2 : 1;
+    if (b_mn && bn / ncta < 64) ncta = 1;        // an MN-major B half-tile must hold whole 64-wide atoms
+    wa.tiles_m = (int)ceil_div(g->m, (int64_t)kTM * ncta);
+    wa.tiles_n = (int)ceil_div(g->n, bn);
+    wa.ntiles = (int64_t)wa.tiles_m * wa.tiles_n * splits;
+    if (ncta == 2) {
+      if (bn == 32) e = launch_ws<32, 5, 2>(wa, st);
+      else if (bn == 64) e = launch_ws<64, 5, 2>(wa, st);
+      else if (bn == 128) e = launch_ws<128, 4, 2>(wa, st);
+      else e = launch_ws<256, 3, 2>(wa, st);
+    } else {
+      if (bn == 32) e = launch_ws<32, 5, 1>(wa, st);
+      else if (bn == 64) e = launch_ws<64, 4, 1>(wa, st);
+      else if (bn == 128) e = launch_ws<128, 3, 1>(wa, st);
+      else e = launch_ws<256, 2, 1>(wa, st);
+    }
+  } else if (bn == 32) e = short_k ? launch_planes<32, 1>(pa, st) : launch_planes<32, 4>(pa, st);
   else if (bn == 64) e = short_k ? launch_planes<64, 1>(pa, st) : launch_planes<64, 4>(pa, st);
   else if (bn == 128) e = short_k ? launch_planes<128, 1>(pa, st) : launch_planes<128, 3>(pa, st);
   else e = launch_planes<256, 2>(pa, st);

@@ -180,9 +180,10 @@ def test_optimizers(cuda):
 @pytest.mark.parametrize("m,n,k", [(128, 128, 64), (1, 1, 1), (257, 256, 845), (130, 64, 128), (1000, 1, 64),
                                    (64, 300, 7), (4096, 256, 848), (300, 40, 200)])
 @pytest.mark.parametrize("ta,tb", [(False, False), (False, True), (True, False), (True, True)])
-@pytest.mark.parametrize("variant", [1, 2, 3])   # 1: split in the GEMM producers, 2: K-major planes, 3: + MN-major
+@pytest.mark.parametrize("variant", [1, 2, 3, 4])   # 1: split in the GEMM producers, 2: K-major planes,
 def test_gemm_bf16x3_tensor_core(cuda, m, n, k, ta, tb, variant):
-    """tcgen05 split-bf16 GEMM: error bound ~2^-16 relative to sum |a||b|."""
+    """tcgen05 split-bf16 GEMM: error bound ~2^-16 relative to sum |a||b|.
+    Variants: 3 = + MN-major planes, 4 = persistent warp-specialised CTA-pair kernel (cta_group::2)."""
     K, L = _kern()
     rng = np.random.RandomState(m + 3 * n + k)
     a = _r(rng, *((k, m) if ta else (m, k)))
@@ -201,7 +202,8 @@ def test_gemm_bf16x3_tensor_core(cuda, m, n, k, ta, tb, variant):
                                    (845, 256, 4100), (4096, 845, 256), (515, 384, 130)])
 @pytest.mark.parametrize("ta,tb", [(False, False), (False, True), (True, False), (True, True)])
 @pytest.mark.parametrize("given", ["a", "b", "ab"])
-def test_gemm_bf16x3_with_caller_planes(cuda, m, n, k, ta, tb, given):
+@pytest.mark.parametrize("variant", [3, 4])
+def test_gemm_bf16x3_with_caller_planes(cuda, m, n, k, ta, tb, given, variant):
     """b2ctr_split_planes output handed to b2ctr_gemm (a_planes / b_planes) must give the same result as
     the GEMM splitting its operands itself: the planes are a pure function of the stored matrix."""
     K, L = _kern()
@@ -211,19 +213,42 @@ def test_gemm_bf16x3_with_caller_planes(cuda, m, n, k, ta, tb, given):
     ap = K.split_planes(a) if "a" in given else None
     bp = K.split_planes(b) if "b" in given else None
     sk = 4 if k > 2048 else 1
-    want = K.gemm(a, b, trans_a=ta, trans_b=tb, precision=L.GEMM_BF16X3, m=m, n=n, k=k, split_k=sk, variant=3)
-    got = K.gemm(a, b, trans_a=ta, trans_b=tb, precision=L.GEMM_BF16X3, m=m, n=n, k=k, split_k=sk, variant=3,
+    want = K.gemm(a, b, trans_a=ta, trans_b=tb, precision=L.GEMM_BF16X3, m=m, n=n, k=k, split_k=sk, variant=variant)
+    got = K.gemm(a, b, trans_a=ta, trans_b=tb, precision=L.GEMM_BF16X3, m=m, n=n, k=k, split_k=sk, variant=variant,
                  a_planes=ap, b_planes=bp)
     assert torch.equal(want, got)
     # strided source (leading window of a wider buffer), as ops.dense passes the embedding concat buffer
     wide = torch.zeros((a.shape[0], a.shape[1] + 5), device=cuda)
     wide[:, :a.shape[1]] = a
     got2 = K.gemm(wide[:, :a.shape[1]], b, trans_a=ta, trans_b=tb, precision=L.GEMM_BF16X3, m=m, n=n, k=k,
-                  split_k=sk, variant=3, a_planes=K.split_planes(wide[:, :a.shape[1]]), b_planes=bp)
+                  split_k=sk, variant=variant, a_planes=K.split_planes(wide[:, :a.shape[1]]), b_planes=bp)
     assert torch.equal(want, got2)
 
 
-@pytest.mark.parametrize("variant", [1, 2, 3])
+@pytest.mark.parametrize("m,n,k,ta,tb,sk", [(40000, 256, 845, False, False, 1), (40000, 845, 256, False, True, 1),
+                                             (845, 256, 40000, True, False, 18), (30000, 128, 256, False, False, 1),
+                                             (30000, 64, 128, False, True, 1), (20000, 40, 100, False, False, 1),
+                                             (256, 256, 30000, True, False, 37)])
+def test_gemm_bf16x3_persistent_pair_many_tiles(cuda, m, n, k, ta, tb, sk):
+    """Variant 4 at shapes where every CTA pair walks many tiles (both TMEM accumulators, several trips
+    round the stage ring): same products in the same K order as the one-tile-per-CTA kernel -> identical."""
+    K, L = _kern()
+    rng = np.random.RandomState(m + n + k)
+    a = _r(rng, *((k, m) if ta else (m, k))).to(cuda)
+    b = _r(rng, *((n, k) if tb else (k, n))).to(cuda)
+    bias = _r(rng, n).to(cuda)
+    kw = dict(trans_a=ta, trans_b=tb, precision=L.GEMM_BF16X3, m=m, n=n, k=k, split_k=sk)
+    if sk == 1:
+        kw.update(bias=bias, act=L.ACT_RELU)
+    want = K.gemm(a, b, variant=3, **kw)
+    for _ in range(3):
+        got = K.gemm(a, b, variant=4, **kw)
+        assert torch.equal(want, got), float((want - got).abs().max())
+    ref = K.gemm(a, b, **{**kw, "precision": L.GEMM_FP32})
+    torch.testing.assert_close(got, ref, rtol=2e-4, atol=2e-3)
+
+
+@pytest.mark.parametrize("variant", [1, 2, 3, 4])
 def test_gemm_bf16x3_splitk_accumulate(cuda, variant):
     K, L = _kern()
     rng = np.random.RandomState(77)

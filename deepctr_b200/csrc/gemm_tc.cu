@@ -1051,9 +1051,9 @@ static int tc_variant(const b2ctr_gemm_t* g) {
   static int mode = -1;
   if (mode < 0) {
     const char* ev = getenv("B2CTR_TC_VARIANT");
-    mode = ev ? atoi(ev) : 3;
+    mode = ev ? atoi(ev) : 4;
   }
-  return (mode >= 1 && mode <= 4) ? mode : 3;
+  return (mode >= 1 && mode <= 4) ? mode : 4;
 }
 
 size_t gemm_bf16x3_workspace_bytes(const b2ctr_gemm_t* g) {

@@ -38,12 +38,11 @@ def _empty(shape, like):
 
 
 def _split_k(m_out, n_out, kred):
-    """wgrad-style GEMMs reduce over the batch: give every SM a slice."""
+    """wgrad-style GEMMs reduce over the batch: one K slice per CTA pair (74 pairs of SMs, 256 x 256 tiles)."""
     if kred < 4096:
         return 1
-    tiles = ((m_out + 127) // 128) * ((n_out + 127) // 128)
-    want = (2 * 148 + tiles - 1) // tiles
-    return int(max(1, min(64, want, kred // 1024)))
+    tiles = ((m_out + 255) // 256) * ((n_out + 255) // 256)
+    return int(max(1, min(74 // tiles if tiles <= 74 else 1, kred // 1024)))
 
 
 def _as2d(x):

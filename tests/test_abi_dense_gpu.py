@@ -245,7 +245,7 @@ def test_gemm_bf16x3_persistent_pair_many_tiles(cuda, m, n, k, ta, tb, sk):
         got = K.gemm(a, b, variant=4, **kw)
         assert torch.equal(want, got), float((want - got).abs().max())
     ref = K.gemm(a, b, **{**kw, "precision": L.GEMM_FP32})
-    torch.testing.assert_close(got, ref, rtol=2e-4, atol=2e-3)
+    torch.testing.assert_close(got, ref, rtol=2e-4, atol=2e-3 * max(1.0, (k / 256.0) ** 0.5))
 
 
 @pytest.mark.parametrize("variant", [1, 2, 3, 4])

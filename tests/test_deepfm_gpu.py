@@ -120,9 +120,14 @@ def test_training_step_graph_replay_matches_eager(cuda):
     x["V"] = rng.randint(0, 30, (n, 4)).astype(np.int32)
     y = rng.randint(0, 2, n).astype(np.float32)
     losses = {}
+    w0 = None
     for mode in ("off", "auto"):
         m = DeepFM(cols, cols, dnn_hidden_units=(16, 8), seed=7)
         m.compile(SGD(0.05), "binary_crossentropy", step_graph=mode)
+        if w0 is None:
+            w0 = [w.copy() for w in m.get_weights()]
+        else:
+            m.set_weights(w0)            # layer names (hence initialiser streams) differ between instances
         h = m.fit(x, y, batch_size=bs, epochs=3, shuffle=False, verbose=0)
         per_batch = [m.test_on_batch({k: v[:bs] for k, v in x.items()}, y[:bs])]
         losses[mode] = (h.history["loss"], per_batch, m)

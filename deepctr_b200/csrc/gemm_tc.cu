@@ -655,14 +655,15 @@ static cudaError_t launch_planes(const PlaneArgs& pa, cudaStream_t st) {
 // (96 KB per 64-deep k-block per SM, ~11 TB/s over 148 SMs).  A CTA pair computes a 256 x BN tile with
 // each CTA staging its own 128 rows of A and only HALF of the B tile (the pair's tensor cores read both
 // halves), i.e. 64 KB per k-block per SM at BN = 256 - which also leaves room for a 3-deep pipeline.
-//   warps 0-3 : epilogue (TMEM -> registers -> global), one TMEM sub-partition each
-//   warps 4-7 : producers (cp.async 16 B chunks into the SWIZZLE_128B stage layout)
-//   warp  8   : TMEM allocation; lane 0 of the LEADER CTA issues every tcgen05.mma of the pair
+//   warps 0-7  : epilogue (TMEM -> registers -> global); warp & 3 = TMEM sub-partition, warp >> 2 = column half
+//   warps 8-11 : producers (cp.async 16 B chunks into the SWIZZLE_128B stage layout)
+//   warp  12   : TMEM allocation; lane 0 of the LEADER CTA issues every tcgen05.mma of the pair
 // TMEM holds two BN-column accumulators: the epilogue of tile i overlaps the main loop of tile i+1.
 // Persistent: grid = min(#tiles, #SMs / NCTA) clusters; tile = cluster id + j * #clusters, N-tile fastest
 // (neighbouring clusters share the A rows through L2).
 // ================================================================================================
-constexpr int kWsThreads = 9 * 32;
+constexpr int kWsEpilogueWarps = 8;
+constexpr int kWsThreads = (kWsEpilogueWarps + 4 + 1) * 32;
 constexpr int kWsProducers = 4;   // warps
 
 struct WsArgs {
@@ -679,13 +680,16 @@ __device__ __forceinline__ uint32_t cluster_ctarank() {
 __device__ __forceinline__ void cluster_sync_all() {
   asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
 }
-// arrive on the barrier at the same shared-memory offset in CTA `cta` of the cluster
+// arrive on the barrier at the same shared-memory offset in CTA `cta` of the cluster.  Default (.release.cta)
+// semantics on purpose: a cluster-scope release drains every outstanding cp.async of the warp first, which
+// serialises the stage ring (measured: the peer CTA's producers spent >50% of their time in that arrive); the
+// data being published has already landed (cp.async.wait_group) and been proxy-fenced by the caller.
 __device__ __forceinline__ void mbar_arrive_cluster(uint64_t* bar, uint32_t cta) {
   asm volatile(
       "{\n\t"
       ".reg .b32 ra;\n\t"
       "mapa.shared::cluster.u32 ra, %0, %1;\n\t"
-      "mbarrier.arrive.release.cluster.shared::cluster.b64 _, [ra];\n\t"
+      "mbarrier.arrive.shared::cluster.b64 _, [ra];\n\t"
       "}\n" ::"r"(smem_u32(bar)),
       "r"(cta)
       : "memory");
@@ -758,11 +762,11 @@ __global__ void __launch_bounds__(kWsThreads, 1) gemm_planes_ws_kernel(const __g
     }
     for (int a = 0; a < 2; ++a) {
       mbar_init(&acc_full[a], 1);
-      mbar_init(&acc_empty[a], 4 * NCTA);             // used on the leader only
+      mbar_init(&acc_empty[a], kWsEpilogueWarps * NCTA);   // used on the leader only
     }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
-  if (warp == 8) {
+  if (warp == kWsEpilogueWarps + kWsProducers) {
     if constexpr (NCTA == 1) {
       asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_slot)),
                    "r"(TMEM_COLS)
@@ -792,9 +796,10 @@ __global__ void __launch_bounds__(kWsThreads, 1) gemm_planes_ws_kernel(const __g
     nkb = kend > kbeg ? (int)((kend - kbeg) / kTK) : 0;
   };
 
-  if (warp >= 4 && warp < 4 + kWsProducers) {
+  constexpr int kMmaWarp = kWsEpilogueWarps + kWsProducers;
+  if (warp >= kWsEpilogueWarps && warp < kMmaWarp) {
     // ------------------------------------------------------------------------------ producers
-    const int tid = threadIdx.x - 128;
+    const int tid = threadIdx.x - kWsEpilogueWarps * 32;
     constexpr int NT = kWsProducers * 32;
     int64_t tile = cluster_id, mt = 0, nt = 0, kbeg = 0;
     int nkb = 0, kb = 0;
@@ -805,6 +810,19 @@ __global__ void __launch_bounds__(kWsThreads, 1) gemm_planes_ws_kernel(const __g
     }
     uint32_t issued = 0, published = 0;
     for (uint32_t it = 0; tile < w.ntiles || published < issued; ++it) {
+      // (1) publish the block issued STAGES-1 iterations ago BEFORE blocking on a free stage: the MMA issuer
+      //     then always has the next block ready while this warp waits for the oldest stage to drain
+      if (it >= STAGES - 1 && published < issued) {
+        asm volatile("cp.async.wait_group %0;" ::"n"(STAGES - 2) : "memory");
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic-proxy writes -> tensor core
+        __syncwarp();
+        if (lane == 0) {
+          if (NCTA == 1 || cta_rank == 0) mbar_arrive(&full_bar[published % STAGES]);
+          else mbar_arrive_cluster(&full_bar[published % STAGES], 0);
+        }
+        ++published;
+      }
+      // (2) refill the stage the MMAs of block it-STAGES have drained
       if (tile < w.ntiles) {
         const int s = it % STAGES;
         mbar_wait(&empty_bar[s], ((it / STAGES) & 1) ^ 1);
@@ -856,15 +874,8 @@ __global__ void __launch_bounds__(kWsThreads, 1) gemm_planes_ws_kernel(const __g
         }
       }
       asm volatile("cp.async.commit_group;" ::: "memory");
-      if (it >= STAGES - 1 && published < issued) {
-        asm volatile("cp.async.wait_group %0;" ::"n"(STAGES - 1) : "memory");
-        asm volatile("fence.proxy.async;" ::: "memory");   // generic-proxy writes -> visible to the tensor core
-        __syncwarp();
-        if (lane == 0) mbar_arrive_cluster(&full_bar[published % STAGES], 0);
-        ++published;
-      }
     }
-  } else if (warp == 8) {
+  } else if (warp == kMmaWarp) {
     // ------------------------------------------------------------------------------ MMA issuer
     if (cta_rank == 0) {
       const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(BN >> 3) << 17) |
@@ -905,7 +916,10 @@ __global__ void __launch_bounds__(kWsThreads, 1) gemm_planes_ws_kernel(const __g
     }
   } else {
     // ------------------------------------------------------------------------------ epilogue
-    const int sub = warp;   // warps 0-3 own TMEM lanes [32*warp, 32*warp + 32)
+    // 8 warps: warp & 3 = TMEM sub-partition (32 rows), warp >> 2 = column half of the accumulator
+    const int sub = warp & 3, half = warp >> 2;
+    constexpr int HALVES = BN >= 64 ? 2 : 1;
+    constexpr int COLS = BN / HALVES;
     const bool vec_c = (g.ldc % 4 == 0) && ((reinterpret_cast<uintptr_t>(g.c) & 15) == 0) &&
                        (!g.bias || (reinterpret_cast<uintptr_t>(g.bias) & 15) == 0);
     const bool vec_ws = (g.n % 4 == 0);
@@ -921,29 +935,30 @@ __global__ void __launch_bounds__(kWsThreads, 1) gemm_planes_ws_kernel(const __g
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
       }
       const int64_t gm = (mt * NCTA + cta_rank) * kTM + sub * 32 + lane;
+      if (half < HALVES) {
 #pragma unroll 1
-      for (int c0 = 0; c0 < BN; c0 += 32) {
-        const int64_t gn0 = nt * BN + c0;
-        if (gn0 >= g.n) break;           // warp-uniform
-        uint32_t r[32];
-        if (nkb > 0) {
-          const uint32_t taddr = tmem_base + ((uint32_t)(sub * 32) << 16) + ab * BN + (uint32_t)c0;
-          asm volatile(
-              "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
-              "{%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,"
-              "%16,%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,%29,%30,%31}, [%32];\n"
-              : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]),
-                "=r"(r[7]), "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]),
-                "=r"(r[14]), "=r"(r[15]), "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]),
-                "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]),
-                "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
-              : "r"(taddr));
-          asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-        } else {
+        for (int c0 = half * COLS; c0 < (half + 1) * COLS; c0 += 32) {
+          const int64_t gn0 = nt * BN + c0;
+          if (gn0 >= g.n) break;           // warp-uniform
+          uint32_t r[32];
+          if (nkb > 0) {
+            const uint32_t taddr = tmem_base + ((uint32_t)(sub * 32) << 16) + ab * BN + (uint32_t)c0;
+            asm volatile(
+                "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+                "{%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,"
+                "%16,%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,%29,%30,%31}, [%32];\n"
+                : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]),
+                  "=r"(r[7]), "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]),
+                  "=r"(r[14]), "=r"(r[15]), "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]),
+                  "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]),
+                  "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+                : "r"(taddr));
+            asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+          } else {
 #pragma unroll
-          for (int j = 0; j < 32; ++j) r[j] = 0u;
-        }
-        if (gm < g.m) {
+            for (int j = 0; j < 32; ++j) r[j] = 0u;
+          }
+          if (gm >= g.m) continue;
           if (g.splits > 1) {
             float* wrow = g.ws + (z * g.m + gm) * g.n + gn0;
             if (vec_ws && gn0 + 32 <= g.n) {
@@ -959,6 +974,7 @@ __global__ void __launch_bounds__(kWsThreads, 1) gemm_planes_ws_kernel(const __g
             }
           } else if (vec_c && gn0 + 32 <= g.n) {
             float* crow = g.c + gm * g.ldc + gn0;
+            const bool relu = g.act == B2CTR_ACT_RELU, other = g.act != B2CTR_ACT_NONE && !relu;
 #pragma unroll
             for (int j = 0; j < 32; j += 4) {
               float4 v = make_float4(g.alpha * __uint_as_float(r[j]), g.alpha * __uint_as_float(r[j + 1]),
@@ -971,8 +987,12 @@ __global__ void __launch_bounds__(kWsThreads, 1) gemm_planes_ws_kernel(const __g
                 const float4 bb = __ldg(reinterpret_cast<const float4*>(g.bias + gn0 + j));
                 v.x += bb.x; v.y += bb.y; v.z += bb.z; v.w += bb.w;
               }
-              v.x = act_apply(v.x, g.act); v.y = act_apply(v.y, g.act);
-              v.z = act_apply(v.z, g.act); v.w = act_apply(v.w, g.act);
+              if (relu) {
+                v.x = fmaxf(v.x, 0.f); v.y = fmaxf(v.y, 0.f); v.z = fmaxf(v.z, 0.f); v.w = fmaxf(v.w, 0.f);
+              } else if (other) {
+                v.x = act_apply(v.x, g.act); v.y = act_apply(v.y, g.act);
+                v.z = act_apply(v.z, g.act); v.w = act_apply(v.w, g.act);
+              }
               *reinterpret_cast<float4*>(crow + j) = v;
             }
           } else {
@@ -992,7 +1012,10 @@ __global__ void __launch_bounds__(kWsThreads, 1) gemm_planes_ws_kernel(const __g
       if (nkb > 0) {      // hand the accumulator back to the MMA issuer of the pair
         asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
         __syncwarp();
-        if (lane == 0) mbar_arrive_cluster(&acc_empty[ab], 0);
+        if (lane == 0) {
+          if (NCTA == 1 || cta_rank == 0) mbar_arrive(&acc_empty[ab]);
+          else mbar_arrive_cluster(&acc_empty[ab], 0);
+        }
         ++acc_it;
       }
     }
@@ -1000,7 +1023,7 @@ __global__ void __launch_bounds__(kWsThreads, 1) gemm_planes_ws_kernel(const __g
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
   __syncthreads();
   if constexpr (NCTA > 1) cluster_sync_all();      // no CTA leaves while its peer may still signal it
-  if (warp == 8) {
+  if (warp == kWsEpilogueWarps + kWsProducers) {
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
     if constexpr (NCTA == 1)
       asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(TMEM_COLS) : "memory");
@@ -1012,7 +1035,7 @@ __global__ void __launch_bounds__(kWsThreads, 1) gemm_planes_ws_kernel(const __g
 template <int BN, int STAGES, int NCTA>
 static cudaError_t launch_ws(const WsArgs& wa, cudaStream_t st) {
   constexpr size_t smem = (size_t)STAGES * (2 * kTM * 128 + 2 * (BN / NCTA) * 128) + 1024;
-  static_assert(smem <= 227 * 1024, "stage ring exceeds shared memory");
+  static_assert(smem + 256 <= 227 * 1024, "stage ring exceeds shared memory");
   auto kern = gemm_planes_ws_kernel<BN, STAGES, NCTA>;
   cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) return e;

@@ -76,6 +76,7 @@ SIGNATURES = {
     "b2ctr_hash64": (_i32, [_vp, _i32, _i64, _i64, _i32, _vp, _vp]),
     "b2ctr_init_normal": (_i32, [_vp, _i64, _f32, _f32, _u64, _vp]),
     "b2ctr_gemm_workspace_bytes": (_sz, [C.POINTER(Gemm)]),
+    "b2ctr_host_pack": (_i32, [C.POINTER(C.c_void_p), C.POINTER(C.c_int64), C.POINTER(C.c_int64), _i32, _vp, _i32]),
     "b2ctr_gemm": (_i32, [C.POINTER(Gemm), _vp, _sz, _vp]),
     "b2ctr_planes_bytes": (_sz, [_i64, _i64]),
     "b2ctr_split_planes": (_i32, [_vp, _i64, _i64, _i64, _vp, _vp]),

@@ -19,6 +19,8 @@ scatter (+ SGD update) launch.
 from collections import defaultdict, OrderedDict
 from itertools import chain
 
+import ctypes as C
+
 import numpy as np
 import torch
 
@@ -788,6 +790,27 @@ class Feeder(object):
             bufs[1] = torch.empty(max(n, 1), dtype=dtype, device=E.device())
         return bufs[0][:n].reshape(shape), bufs[1][:n].reshape(shape)
 
+    def _fill(self, sn, items, b):
+        """Copy every input's [b, w] block into the flat pinned buffer: one b2ctr_host_pack call (persistent
+        native thread pool, no GIL) - a single core moves ~6 GB/s, which would otherwise cap the input
+        pipeline at ~1.7 ms per 10 MB batch, above the ~1.3 ms training step it feeds."""
+        n = len(items)
+        keep = []
+        src = (C.c_void_p * n)()
+        nbytes = (C.c_int64 * n)()
+        offs = (C.c_int64 * n)()
+        off = 0
+        isz = sn.itemsize
+        for i, (name, a, w) in enumerate(items):
+            if not (a.flags.c_contiguous and a.dtype == sn.dtype):
+                a = np.ascontiguousarray(a, dtype=sn.dtype)
+                keep.append(a)
+            src[i] = a.ctypes.data
+            nbytes[i] = b * w * isz
+            offs[i] = off * isz
+            off += b * w
+        L.check(L.lib().b2ctr_host_pack(src, nbytes, offs, n, C.c_void_p(sn.ctypes.data), 0), "host_pack")
+
     def _upload(self, host, dev):
         dev.copy_(host, non_blocking=True)
         ev = self._copied_ev.get(self.slot)
@@ -838,11 +861,7 @@ class Feeder(object):
                 # ids: one flat staging buffer of per-input contiguous blocks (a plain memcpy per input on
                 # the host, one H2D for all); the gather kernels take a pointer + stride per feature
                 stage, dbuf = self._stage(key, (b * total,), th_dt[key])
-                sn = stage.numpy()
-                off = 0
-                for name, a, w in items:
-                    sn[off:off + b * w].reshape(b, w)[...] = a
-                    off += b * w
+                self._fill(stage.numpy(), items, b)
                 pack = self._upload(stage, dbuf)
                 off = 0
                 for name, a, w in items:
@@ -856,11 +875,7 @@ class Feeder(object):
             # floats: contiguous per-input blocks on the host (plain memcpy), one H2D, then a device kernel
             # builds the row-major [B, total] dense pack (a strided host-side pack costs ~2 ms at B = 65536)
             stage, dbuf = self._stage(key, (b * total,), th_dt[key])
-            sn = stage.numpy()
-            off = 0
-            for name, a, w in items:
-                sn[off:off + b * w].reshape(b, w)[...] = a
-                off += b * w
+            self._fill(stage.numpy(), items, b)
             flat = self._upload(stage, dbuf)
             if len(items) > 64:
                 raise ValueError("more than 64 dense inputs are not supported")

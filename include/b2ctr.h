@@ -48,6 +48,13 @@ B2CTR_API const char* b2ctr_last_error(void);
 B2CTR_API int64_t b2ctr_launch_count(void);
 B2CTR_API void b2ctr_reset_launch_count(void);
 
+/* Host-side input staging (no GPU work): copy n blocks src[i][0 .. nbytes[i]) to dst + dst_off[i] with a
+ * persistent pool of `threads` helper threads (0 = pick from the core count, 1 = inline memcpy).  Replaces the
+ * per-feature numpy -> tensor conversion of Keras' data adapter behind model.fit(model_input, y)
+ * (reference examples/run_classification_criteo.py:48); the caller uploads dst with one cudaMemcpyAsync. */
+B2CTR_API b2ctr_status_t b2ctr_host_pack(const void* const* src, const int64_t* nbytes, const int64_t* dst_off,
+                                         int32_t n, void* dst, int32_t threads);
+
 /* ------------------------------------------------------------------------------------------ */
 /* 1. Embedding gather / scatter-update                                                        */
 /*    replaces: tf.keras.layers.Embedding call in deepctr/inputs.py:101-130 (embedding_lookup,  */

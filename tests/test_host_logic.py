@@ -157,3 +157,30 @@ def test_compute_path_fails_loudly_without_cuda():
     x = {c.name: np.zeros(4, np.int32 if c.name[0] == "C" else np.float32) for c in cols}
     with pytest.raises(B2ctrError, match="no CPU fallback|CUDA"):
         model.predict(x, batch_size=4)
+
+
+def test_host_pack_native_thread_pool():
+    """b2ctr_host_pack (host-only entry point of the C-ABI): blocks land at their offsets, for the inline
+    path (small), the pooled path (large, split across workers inside blocks) and empty input."""
+    import ctypes as C
+    from deepctr_b200 import _lib as L
+    rng = np.random.RandomState(0)
+    for sizes, threads in [([10, 0, 7], 0), ([300000, 1, 65536 * 4, 12345, 65536 * 8], 0),
+                           ([1 << 20, 1 << 20, 3], 3), ([1 << 21], 1), ([], 0)]:
+        blocks = [rng.randint(0, 255, s).astype(np.uint8) for s in sizes]
+        n = len(blocks)
+        gap = 5
+        offs, off = [], 0
+        for s in sizes:
+            offs.append(off)
+            off += s + gap
+        dst = np.full(off + 1, 255, np.uint8)
+        src = (C.c_void_p * max(n, 1))(*[b.ctypes.data for b in blocks])
+        nb = (C.c_int64 * max(n, 1))(*sizes)
+        of = (C.c_int64 * max(n, 1))(*offs)
+        L.check(L.lib().b2ctr_host_pack(src, nb, of, n, C.c_void_p(dst.ctypes.data), threads), "host_pack")
+        for b, o in zip(blocks, offs):
+            assert (dst[o:o + len(b)] == b).all()
+            assert (dst[o + len(b):o + len(b) + gap] == 255).all()      # nothing written between blocks
+    with pytest.raises(ValueError):
+        L.check(L.lib().b2ctr_host_pack(None, None, None, 2, None, 0), "host_pack")

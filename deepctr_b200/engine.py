@@ -1194,16 +1194,24 @@ class Model(object):
             nsteps = (n + batch_size - 1) // batch_size
             # every step's loss is read back (4 B, asynchronous D2H into pinned memory); the host only
             # waits at the end of the epoch, so staging batch i+1 overlaps the kernels of batch i
-            host_losses = torch.empty((max(nsteps, 1),), dtype=torch.float32)
-            try:
-                host_losses = host_losses.pin_memory()
-            except Exception:
-                pass
-            # batch i+1 is packed and copied H2D by a helper thread on a side stream while the kernels of
-            # batch i are being launched / run
-            from concurrent.futures import ThreadPoolExecutor
-            if not hasattr(self, "_stage_pool"):
-                self._stage_pool = ThreadPoolExecutor(1)
+            host_losses = getattr(self, "_host_losses", None)
+            if host_losses is None or host_losses.numel() < nsteps:
+                host_losses = torch.empty((max(nsteps, 64),), dtype=torch.float32)
+                try:
+                    host_losses = host_losses.pin_memory()
+                except Exception:
+                    pass
+                self._host_losses = host_losses
+            # Input pipeline: a producer thread packs batch after batch into the staging ring (native
+            # thread-pool memcpy into pinned memory + H2D on a side stream) and runs AHEAD of this thread by up
+            # to RING-1 batches; this thread only replays the step graph per staged batch.  The semaphore
+            # counts launched steps: ring slot (j mod RING) is refilled only after step j-RING was enqueued
+            # (its `consumed` event then orders the H2D after the kernels that read the slot).
+            import queue
+            import sys
+            import threading
+            from .inputs import Feeder
+            if not hasattr(self, "_stage_stream"):
                 self._stage_stream = torch.cuda.Stream()
             starts = list(range(0, n, batch_size))
 
@@ -1212,23 +1220,48 @@ class Model(object):
                 return slice_inputs(x, idx), y[idx]
 
             self._materialize()
+            if self._feeder is None:
+                self._feeder = Feeder(self)
             dev_index = torch.cuda.current_device()
+            staged_q = queue.Queue()
+            permits = threading.Semaphore(Feeder._RING - 1)
+            stop = [False]
 
-            def stage(s):
-                torch.cuda.set_device(dev_index)
-                bx, by = batch_of(s)
-                return self._stage_batch(bx, by, self._stage_stream)
+            def producer():
+                try:
+                    torch.cuda.set_device(dev_index)
+                    for s in starts:
+                        permits.acquire()
+                        if stop[0]:
+                            return
+                        bx, by = batch_of(s)
+                        staged_q.put(self._stage_batch(bx, by, self._stage_stream))
+                except BaseException as exc:       # surfaced by the consumer loop
+                    staged_q.put(exc)
 
-            fut = self._stage_pool.submit(stage, starts[0]) if starts else None
-            for i, s in enumerate(starts):
-                staged = fut.result()
-                fut = self._stage_pool.submit(stage, starts[i + 1]) if i + 1 < len(starts) else None
-                ls, _, b = self._loss_step(None, None, True, staged=staged)
-                # (graph replay: `ls` is the graph's static output; the copy below is stream-ordered before
-                # the next replay overwrites it)
-                host_losses[i:i + 1].copy_(ls, non_blocking=True)
-                cnt += b
-            torch.cuda.synchronize()
+            worker = threading.Thread(target=producer, name="b2ctr-staging", daemon=True)
+            # the producer spends most of its time in GIL-releasing copies; a short switch interval keeps its
+            # Python stretches from holding the interpreter while this thread needs ~0.1 ms per step
+            switch0 = sys.getswitchinterval()
+            sys.setswitchinterval(1e-4)
+            worker.start()
+            try:
+                for i, s in enumerate(starts):
+                    staged = staged_q.get()
+                    if isinstance(staged, BaseException):
+                        raise staged
+                    ls, _, b = self._loss_step(None, None, True, staged=staged)
+                    permits.release()
+                    # (graph replay: `ls` is the graph's static output; the copy below is stream-ordered
+                    # before the next replay overwrites it)
+                    host_losses[i:i + 1].copy_(ls, non_blocking=True)
+                    cnt += b
+                torch.cuda.synchronize()
+            finally:
+                stop[0] = True
+                permits.release()
+                worker.join()
+                sys.setswitchinterval(switch0)
             self.d2h_bytes = getattr(self, "d2h_bytes", 0) + 4 * nsteps
             tot = float(host_losses[:nsteps].double().sum()) if nsteps else 0.0
             logs = {"loss": tot / max(cnt, 1) + self._reg_loss()}

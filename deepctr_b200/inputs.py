@@ -735,7 +735,13 @@ class Feeder(object):
         for s in model.planner.slots:
             if s.hash[1] is not None:
                 self.host_hash[s.input_name] = s.hash[1]
+        self._meta = {}
+        for name, spec in self.specs.items():
+            tail = tuple(int(d) for d in spec.shape[1:])
+            width = int(np.prod(tail)) if tail else 1
+            self._meta[name] = (width, spec.dtype in ("float32", "float64", "float16"), spec.dtype == "int64", tail)
         self._pinned = {}
+        self._views = {}
         self._copied_ev = {}
         self._consumed_ev = {}
         self.h2d_bytes = 0
@@ -778,7 +784,9 @@ class Feeder(object):
 
     def _stage(self, key, shape, dtype):
         """(pinned host view, device view) of the current slot for dtype group `key`."""
-        n = int(np.prod(shape))
+        n = 1
+        for d in shape:
+            n *= int(d)
         bufs = self._pinned.setdefault((key, self.slot), [None, None])
         if bufs[0] is None or bufs[0].numel() < n:
             host = torch.empty(max(n, 1), dtype=dtype)
@@ -788,6 +796,7 @@ class Feeder(object):
                 pass
             bufs[0] = host
             bufs[1] = torch.empty(max(n, 1), dtype=dtype, device=E.device())
+            self._views.clear()          # cached per-slot views point at the replaced buffer
         return bufs[0][:n].reshape(shape), bufs[1][:n].reshape(shape)
 
     def _fill(self, sn, items, b):
@@ -805,7 +814,7 @@ class Feeder(object):
             if not (a.flags.c_contiguous and a.dtype == sn.dtype):
                 a = np.ascontiguousarray(a, dtype=sn.dtype)
                 keep.append(a)
-            src[i] = a.ctypes.data
+            src[i] = a.__array_interface__["data"][0]
             nbytes[i] = b * w * isz
             offs[i] = off * isz
             off += b * w
@@ -825,26 +834,30 @@ class Feeder(object):
         self._next_slot()
         groups = {"i32": [], "i64": [], "f32": []}
         arrays = {}
+        meta = self._meta
         for name in self.names:
             if name not in xd:
                 raise ValueError("missing model input %r" % name)
-            spec = self.specs[name]
             a = xd[name]
-            if isinstance(a, torch.Tensor) and a.is_cuda:
-                arrays[name] = ("dev", a)
-                continue
-            a = np.asarray(a.values if hasattr(a, "values") else a)
-            width = int(np.prod(spec.shape[1:])) if len(spec.shape) > 1 else 1
+            width, is_float, want_i64, shape_tail = meta[name]
+            if type(a) is not np.ndarray:
+                if isinstance(a, torch.Tensor) and a.is_cuda:
+                    arrays[name] = ("dev", a)
+                    continue
+                a = np.asarray(a.values if hasattr(a, "values") else a)
             if name in self.host_hash:
                 a = host_hash(a, self.host_hash[name])
-            if a.dtype.kind in ("U", "S", "O"):
+            kind = a.dtype.kind
+            if kind in "USO":
                 raise ValueError("input %r holds strings: declare the SparseFeat with use_hash=True" % name)
-            a = a.reshape(a.shape[0], -1) if a.ndim != 2 or a.shape[1] != width else a
-            if a.shape[1] != width:
-                raise ValueError("input %r: expected %d values per sample, got %s" % (name, width, a.shape))
-            if spec.dtype in ("float32", "float64", "float16"):
+            # hot path (fit over per-feature 1-D columns): no reshape, _fill only needs pointer + contiguity
+            if not (a.ndim == 1 and width == 1) and (a.ndim != 2 or a.shape[1] != width):
+                a = a.reshape(a.shape[0], -1)
+                if a.shape[1] != width:
+                    raise ValueError("input %r: expected %d values per sample, got %s" % (name, width, a.shape))
+            if is_float:
                 groups["f32"].append((name, a, width))
-            elif a.dtype == np.int64 and (spec.dtype == "int64" or a.size and
+            elif a.dtype == np.int64 and (want_i64 or a.size and
                                           (a.max(initial=0) > 2 ** 31 - 1 or a.min(initial=0) < -2 ** 31)):
                 groups["i64"].append((name, a, width))
             else:
@@ -857,26 +870,31 @@ class Feeder(object):
                 continue
             b = items[0][1].shape[0]
             total = sum(w for _, _, w in items)
+            # the device side of a ring slot is persistent, so the per-input views (engine Vars) of a slot
+            # are built once and reused for every batch that lands in it
+            vkey = (self.slot, key, b, tuple(name for name, _, _ in items))
+            cached = self._views.get(vkey)
+            stage, dbuf = self._stage(key, (b * total,), th_dt[key])
+            self._fill(stage.numpy(), items, b)
+            pack = self._upload(stage, dbuf)
             if key != "f32":
                 # ids: one flat staging buffer of per-input contiguous blocks (a plain memcpy per input on
                 # the host, one H2D for all); the gather kernels take a pointer + stride per feature
-                stage, dbuf = self._stage(key, (b * total,), th_dt[key])
-                self._fill(stage.numpy(), items, b)
-                pack = self._upload(stage, dbuf)
-                off = 0
-                for name, a, w in items:
-                    spec = self.specs[name]
-                    shape = (b,) + tuple(int(s) for s in spec.shape[1:])
-                    v = E.Var(pack[off:off + b * w].reshape(shape))
-                    v.name = name
-                    feed[name] = v
-                    off += b * w
+                if cached is None:
+                    cached = {}
+                    off = 0
+                    for name, a, w in items:
+                        shape = (b,) + self._meta[name][3]
+                        v = E.Var(pack[off:off + b * w].reshape(shape))
+                        v.name = name
+                        cached[name] = v
+                        off += b * w
+                    self._views[vkey] = cached
+                feed.update(cached)
                 continue
             # floats: contiguous per-input blocks on the host (plain memcpy), one H2D, then a device kernel
             # builds the row-major [B, total] dense pack (a strided host-side pack costs ~2 ms at B = 65536)
-            stage, dbuf = self._stage(key, (b * total,), th_dt[key])
-            self._fill(stage.numpy(), items, b)
-            flat = self._upload(stage, dbuf)
+            flat = pack
             if len(items) > 64:
                 raise ValueError("more than 64 dense inputs are not supported")
             if len(items) > 1:
@@ -884,23 +902,26 @@ class Feeder(object):
                 pack = K.pack_rows(flat, [w for _, _, w in items], b, out=pbuf)
             else:
                 pack = flat.reshape(b, total)
-            base = E.Var(pack, name="__dense_pack__" if key == "f32" else "__id_pack_%s__" % key)
-            if key == "f32":
-                feed["__dense_pack__"] = base
-            col = 0
-            for name, a, w in items:
-                spec = self.specs[name]
-                shape = (b,) + tuple(int(s) for s in spec.shape[1:])
-                view = pack[:, col:col + w]
-                if key == "f32":
+            if cached is None:
+                cached = {}
+                base = E.Var(pack, name="__dense_pack__")
+                cached["__dense_pack__"] = base
+                col = 0
+                for name, a, w in items:
+                    shape = (b,) + self._meta[name][3]
+                    view = pack[:, col:col + w]
                     v = E.Var(view.as_strided(shape, (pack.stride(0),) + _dense_strides(shape[1:]),
                                               pack.storage_offset() + col),
                               base=base, col0=col, ncols=w)
-                else:
-                    v = E.Var(view)
-                v.name = name
-                feed[name] = v
-                col += w
+                    v.name = name
+                    cached[name] = v
+                    col += w
+                self._views[vkey] = cached
+            else:
+                for v in cached.values():          # per-step state of a reused Var
+                    v.grad = None
+                    v.planes = None
+            feed.update(cached)
         # device-resident inputs: float columns that are views of one [B, nd] buffer form a dense pack
         packs = {}
         for name, (_, a) in arrays.items():

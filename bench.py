@@ -229,7 +229,7 @@ def main():
 
     precision = args.precision
     if precision == "auto":
-        precision = "fp32"
+        precision = "bf16x3"
     ops.set_gemm_precision(precision)
     cols = feature_columns(cfg)
     model = DeepFM(cols, cols, dnn_hidden_units=cfg["hidden"], l2_reg_linear=0, l2_reg_embedding=0, l2_reg_dnn=0)

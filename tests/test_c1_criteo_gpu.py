@@ -13,7 +13,7 @@ from oracle import models as OM
 from oracle import ops as O
 import b2_helpers as H
 
-pytestmark = pytest.mark.gpu
+pytestmark = [pytest.mark.gpu, pytest.mark.usefixtures("gemm_precision")]
 DATA = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "criteo_sample.txt")
 
 

@@ -9,7 +9,7 @@ from oracle import models as OM
 from oracle import ops as O
 import b2_helpers as H
 
-pytestmark = pytest.mark.gpu
+pytestmark = [pytest.mark.gpu, pytest.mark.usefixtures("gemm_precision")]
 
 
 def _build(rng, **kw):

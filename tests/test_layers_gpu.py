@@ -8,7 +8,7 @@ import torch
 from oracle import ops as O
 import b2_helpers as H
 
-pytestmark = pytest.mark.gpu
+pytestmark = [pytest.mark.gpu, pytest.mark.usefixtures("gemm_precision")]
 RTOL, ATOL = 1e-4, 1e-5
 
 
@@ -40,7 +40,13 @@ def _t(a, grad=True):
 
 
 def _close(a, b, rtol=RTOL, atol=ATOL):
-    np.testing.assert_allclose(np.asarray(a), np.asarray(b), rtol=rtol, atol=atol)
+    a, b = np.asarray(a), np.asarray(b)
+    from deepctr_b200 import ops, _lib as L
+    if ops.GEMM_PRECISION == L.GEMM_BF16X3 and b.size:
+        # split-bf16 GEMMs: the error is bounded relative to sum |a||b| of the dot product, not to the
+        # (possibly cancelling) result -> normwise 1e-4 instead of elementwise
+        atol = max(atol, 1e-4 * float(np.abs(b).max()))
+    np.testing.assert_allclose(a, b, rtol=rtol, atol=atol)
 
 
 def test_fm_layer(cuda):

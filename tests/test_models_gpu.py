@@ -8,7 +8,7 @@ from oracle import models as OM
 from oracle import ops as O
 import b2_helpers as H
 
-pytestmark = pytest.mark.gpu
+pytestmark = [pytest.mark.gpu, pytest.mark.usefixtures("gemm_precision")]
 
 
 def _check_step(model, oracle_fn, x, y, lr=0.05, steps=2, tol=3e-3):

@@ -19,4 +19,17 @@ int32_t b2ctr_abi_version(void) { return 1; }
 const char* b2ctr_last_error(void) { return b2ctr::g_err; }
 int64_t b2ctr_launch_count(void) { return (int64_t)b2ctr::g_launches.load(); }
 void b2ctr_reset_launch_count(void) { b2ctr::g_launches.store(0); }
+b2ctr_status_t b2ctr_enable_peer_access(int32_t peer_device) {
+  cudaError_t e = cudaDeviceEnablePeerAccess(peer_device, 0);
+  if (e == cudaErrorPeerAccessAlreadyEnabled) {
+    cudaGetLastError();
+    return B2CTR_OK;
+  }
+  if (e != cudaSuccess) {
+    b2ctr::set_error("enable_peer_access(%d): %s", peer_device, cudaGetErrorString(e));
+    cudaGetLastError();
+    return B2CTR_ERR_CUDA;
+  }
+  return B2CTR_OK;
+}
 }

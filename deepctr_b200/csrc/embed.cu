@@ -395,7 +395,39 @@ struct UniParams {
   int32_t has_lin;
   int32_t l2_hints;
   int32_t store_grads;
+  // row-sharded tables over peer mappings (world = 2^wshift shards): device arrays [nfeat * world]
+  float* const* peer_tab;
+  float* const* peer_lin;
+  int32_t world;
+  int32_t wshift;
 };
+
+// peer (NVLink) accesses: no read-only / L2-policy qualifiers - the line lives in the owner's L2
+__device__ __forceinline__ float4 ld_peer_f4(const float* p) {
+  float4 r;
+  asm volatile("ld.global.L1::no_allocate.v4.f32 {%0,%1,%2,%3}, [%4];"
+               : "=f"(r.x), "=f"(r.y), "=f"(r.z), "=f"(r.w)
+               : "l"(p));
+  return r;
+}
+__device__ __forceinline__ float ld_peer_f1(const float* p) {
+  float r;
+  asm volatile("ld.global.L1::no_allocate.f32 %0, [%1];" : "=f"(r) : "l"(p));
+  return r;
+}
+__device__ __forceinline__ void red_peer_f4(float* p, float4 v) {
+  asm volatile("red.relaxed.sys.global.add.v4.f32 [%0], {%1,%2,%3,%4};" ::"l"(p), "f"(v.x), "f"(v.y), "f"(v.z),
+               "f"(v.w)
+               : "memory");
+}
+__device__ __forceinline__ void red_peer_f1(float* p, float v) {
+  asm volatile("red.relaxed.sys.global.add.f32 [%0], %1;" ::"l"(p), "f"(v) : "memory");
+}
+// shard pointer + local row of global row `id` of feature f
+__device__ __forceinline__ float* shard_row(float* const* tabs, const UniParams& p, int f, int64_t id, int width) {
+  const int64_t own = id & (int64_t)(p.world - 1);
+  return tabs[(int64_t)f * p.world + own] + (id >> p.wshift) * width;
+}
 
 __device__ __forceinline__ int64_t uni_id(const UniParams& p, int f, int64_t b) {
   return load_idx(p.idx[f], b * p.idx_stride[f], p.idx_dtype);
@@ -405,8 +437,8 @@ __device__ __forceinline__ int64_t uni_id(const UniParams& p, int f, int64_t b) 
 // Latency hiding (ncu, profiles/r1_embed_before.txt: 40 % DRAM, 35 % warps active): the id -> row -> store
 // chain is broken by prefetching the NEXT sample's ids before the current rows are requested, and the
 // register budget is capped at 64 (4 CTAs = 32 warps per SM).
-template <int LPR>
-__global__ void __launch_bounds__(256, 4)
+template <int LPR, bool SHARD>
+__global__ void __launch_bounds__(256, SHARD ? 3 : 4)
     gather_uniform_fwd_kernel(const __grid_constant__ UniParams p, int64_t batch) {
   constexpr int RPI = 32 / LPR;
   constexpr int U = 7;   // 7 x RPI(4) = 28 >= 26 Criteo fields in one pass at dim 32
@@ -437,8 +469,12 @@ __global__ void __launch_bounds__(256, 4)
         const int64_t idb = __shfl_sync(0xffffffffu, id1, fs & 31);
         const int64_t id = fs < 32 ? ida : idb;
         if (f < F) {
-          const float* src = p.table[f] + id * dim + chunk * 4;
-          v[u] = hints ? ldg_stream_f4_pol(src, pol_stream) : ldg_stream_f4(src);
+          if (SHARD) {
+            v[u] = ld_peer_f4(shard_row(p.peer_tab, p, f, id, dim) + chunk * 4);
+          } else {
+            const float* src = p.table[f] + id * dim + chunk * 4;
+            v[u] = hints ? ldg_stream_f4_pol(src, pol_stream) : ldg_stream_f4(src);
+          }
         }
       }
 #pragma unroll
@@ -471,8 +507,13 @@ __global__ void __launch_bounds__(256, 4)
     if (p.linear != nullptr) {
       float l = 0.f;
       if (p.has_lin) {
-        if (lane < F) l += hints ? ldg_f1_pol(p.lin[lane] + id0, pol_keep) : p.lin[lane][id0];
-        if (lane + 32 < F) l += hints ? ldg_f1_pol(p.lin[lane + 32] + id1, pol_keep) : p.lin[lane + 32][id1];
+        if (SHARD) {
+          if (lane < F) l += ld_peer_f1(shard_row(p.peer_lin, p, lane, id0, 1));
+          if (lane + 32 < F) l += ld_peer_f1(shard_row(p.peer_lin, p, lane + 32, id1, 1));
+        } else {
+          if (lane < F) l += hints ? ldg_f1_pol(p.lin[lane] + id0, pol_keep) : p.lin[lane][id0];
+          if (lane + 32 < F) l += hints ? ldg_f1_pol(p.lin[lane + 32] + id1, pol_keep) : p.lin[lane + 32][id1];
+        }
       }
       l = warp_sum(l);
       if (lane == 0) p.linear[b] = l;
@@ -490,8 +531,8 @@ __global__ void __launch_bounds__(256, 4)
 
 // Backward: 4 dx + 4 x loads in flight per lane, reds issued as soon as a chunk's gradient is formed
 // (fire-and-forget), ids re-broadcast by shuffle instead of being kept in registers -> 64 registers.
-template <int LPR>
-__global__ void __launch_bounds__(256, 3)
+template <int LPR, bool SHARD>
+__global__ void __launch_bounds__(256, SHARD ? 2 : 3)
     scatter_uniform_bwd_kernel(const __grid_constant__ UniParams p, const float* __restrict__ dx,
                                const float* __restrict__ dfm, const float* __restrict__ dlinear,
                                float scale, float lin_scale, int64_t batch) {
@@ -564,7 +605,8 @@ __global__ void __launch_bounds__(256, 3)
             r.w += gfm * (s.w - xv[u].w);
           }
           r.x *= scale; r.y *= scale; r.z *= scale; r.w *= scale;
-          if (p.store_grads) stg_stream_f4(p.table[f] + id * dim + chunk * 4, r);
+          if (SHARD) red_peer_f4(shard_row(p.peer_tab, p, f, id, dim) + chunk * 4, r);
+          else if (p.store_grads) stg_stream_f4(p.table[f] + id * dim + chunk * 4, r);
           else if (hints) red_add_f4_pol(p.table[f] + id * dim + chunk * 4, r, pol_stream);
           else red_add_f4(p.table[f] + id * dim + chunk * 4, r);
         }
@@ -572,7 +614,10 @@ __global__ void __launch_bounds__(256, 3)
     }
     if (dlinear && p.has_lin) {
       const float gl = dlinear[b] * lin_scale;
-      if (p.store_grads) {
+      if (SHARD) {
+        if (lane < F) red_peer_f1(shard_row(p.peer_lin, p, lane, id0, 1), gl);
+        if (lane + 32 < F) red_peer_f1(shard_row(p.peer_lin, p, lane + 32, id1, 1), gl);
+      } else if (p.store_grads) {
         if (lane < F) p.lin[lane][id0] = gl;
         if (lane + 32 < F) p.lin[lane + 32][id1] = gl;
       } else {
@@ -706,12 +751,23 @@ static b2ctr_status_t fill_uni(const b2ctr_uniform_gather_t* g, UniParams* p) {
     B2_REQUIRE(ft.dim == dim && ft.maxlen == 1 && ft.hash_mode == B2CTR_HASH_NONE,
                "uniform gather: feature %d is not a plain single-valued feature of dim %d", f, dim);
     B2_REQUIRE(ft.idx_dtype == g->feats[0].idx_dtype, "uniform gather: mixed idx dtypes");
-    B2_REQUIRE(ft.table && ft.idx && aligned16(ft.table), "uniform gather: feature %d bad pointers", f);
+    B2_REQUIRE(ft.idx && (g->world > 1 || (ft.table && aligned16(ft.table))),
+               "uniform gather: feature %d bad pointers", f);
     p->table[f] = ft.table;
     p->idx[f] = ft.idx;
     p->idx_stride[f] = ft.idx_stride;
-    p->lin[f] = g->lin_tables ? g->lin_tables[f] : nullptr;
-    B2_REQUIRE(!g->lin_tables || p->lin[f], "uniform gather: lin_tables[%d] is NULL", f);
+    p->lin[f] = (g->lin_tables && g->world <= 1) ? g->lin_tables[f] : nullptr;
+    B2_REQUIRE(g->world > 1 || !g->lin_tables || p->lin[f], "uniform gather: lin_tables[%d] is NULL", f);
+  }
+  p->world = g->world > 1 ? g->world : 1;
+  p->wshift = 0;
+  p->peer_tab = g->peer_tables;
+  p->peer_lin = g->peer_lin_tables;
+  if (g->world > 1) {
+    B2_REQUIRE((g->world & (g->world - 1)) == 0, "uniform gather: world must be a power of two (got %d)", g->world);
+    B2_REQUIRE(g->peer_tables, "uniform gather: world > 1 needs peer_tables");
+    B2_REQUIRE(!(g->flags & B2CTR_UNIFORM_STORE_GRADS), "uniform gather: STORE_GRADS is not defined for sharded tables");
+    while ((1 << p->wshift) < g->world) ++p->wshift;
   }
   p->dense = g->dense;
   p->x = g->x;
@@ -726,7 +782,7 @@ static b2ctr_status_t fill_uni(const b2ctr_uniform_gather_t* g, UniParams* p) {
   p->ndense = g->ndense;
   p->dim = dim;
   p->idx_dtype = g->feats[0].idx_dtype;
-  p->has_lin = g->lin_tables != nullptr;
+  p->has_lin = g->world > 1 ? (g->peer_lin_tables != nullptr) : (g->lin_tables != nullptr);
   static int hints = -1;
   if (hints < 0) { const char* ev = getenv("B2CTR_L2_HINTS"); hints = ev ? atoi(ev) : 1; }
   p->l2_hints = hints;
@@ -776,15 +832,18 @@ b2ctr_status_t b2ctr_embed_scatter_add(const b2ctr_feature_t* feats, int32_t nfe
   return B2CTR_OK;
 }
 
-#define B2_DISPATCH_LPR(KERNEL, dim, ...)                                      \
+#define B2_DISPATCH_LPR1(KERNEL, SH, dim, ...)                                 \
   switch ((dim) / 4) {                                                         \
-    case 1: KERNEL<1><<<grid, 256, 0, st>>>(__VA_ARGS__); break;               \
-    case 2: KERNEL<2><<<grid, 256, 0, st>>>(__VA_ARGS__); break;               \
-    case 4: KERNEL<4><<<grid, 256, 0, st>>>(__VA_ARGS__); break;               \
-    case 8: KERNEL<8><<<grid, 256, 0, st>>>(__VA_ARGS__); break;               \
-    case 16: KERNEL<16><<<grid, 256, 0, st>>>(__VA_ARGS__); break;             \
-    default: KERNEL<32><<<grid, 256, 0, st>>>(__VA_ARGS__); break;             \
+    case 1: KERNEL<1, SH><<<grid, 256, 0, st>>>(__VA_ARGS__); break;           \
+    case 2: KERNEL<2, SH><<<grid, 256, 0, st>>>(__VA_ARGS__); break;           \
+    case 4: KERNEL<4, SH><<<grid, 256, 0, st>>>(__VA_ARGS__); break;           \
+    case 8: KERNEL<8, SH><<<grid, 256, 0, st>>>(__VA_ARGS__); break;           \
+    case 16: KERNEL<16, SH><<<grid, 256, 0, st>>>(__VA_ARGS__); break;         \
+    default: KERNEL<32, SH><<<grid, 256, 0, st>>>(__VA_ARGS__); break;         \
   }
+#define B2_DISPATCH_LPR(KERNEL, dim, ...)                                      \
+  if (p.world > 1) { B2_DISPATCH_LPR1(KERNEL, true, dim, __VA_ARGS__) }        \
+  else { B2_DISPATCH_LPR1(KERNEL, false, dim, __VA_ARGS__) }
 
 b2ctr_status_t b2ctr_embed_gather_uniform_fwd(const b2ctr_uniform_gather_t* g, int64_t batch,
                                               void* stream) {

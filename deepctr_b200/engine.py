@@ -1050,8 +1050,11 @@ class Model(object):
     # ---- CUDA-graph replay of the training step ---------------------------------------------------
     def _graph_eligible(self):
         from . import ops
-        if self.step_graph in (False, None, "off") or K.PROFILE is not None or getattr(self, "dist", None) is not None:
+        if self.step_graph in (False, None, "off") or K.PROFILE is not None:
             return False
+        if getattr(self, "dist", None) is not None and getattr(self.planner, "sharded", False) \
+                and not getattr(self.planner, "peer_mode", False):
+            return False                       # NCCL all-to-all transport: split sizes are read on the host
         if self.optimizer.name == "adam":      # step-dependent bias correction is a by-value kernel argument
             return False
         return ops.UNCAPTURABLE == self._uncapturable0

@@ -426,6 +426,24 @@ class EmbeddingPlanner(object):
         self.sharded = True
         if lin_ok:
             self.lin_hint = True     # the linear rows never leave their owner: only the per-sample sum exists
+        import os
+        mode = os.environ.get("B2CTR_SHARD_MODE", "peer")
+        pow2 = ctx.world & (ctx.world - 1) == 0
+        self.peer_mode = mode == "peer" and pow2 and ctx.backend == "nccl"
+        self.peers = None            # built lazily (tables must be materialised on the device first)
+
+    def _peer_tables(self, fast_slots, lin_fused):
+        """(PeerTables of the embedding shards, PeerTables of the linear shards | None), built once."""
+        if self.peers is None:
+            from . import parallel
+            tabs = [s.emb.embeddings.materialize() for s in fast_slots]
+            emb = parallel.PeerTables(self.dist, tabs, L)
+            lin = None
+            if lin_fused:
+                lin = parallel.PeerTables(self.dist, [s.emb.embeddings.materialize().reshape(-1) for s in self.lin], L)
+            token = torch.zeros((1,), dtype=torch.float32, device=tabs[0].device)
+            self.peers = (emb, lin, token)
+        return self.peers
 
     def _fast_eligible(self):
         m = self.main
@@ -488,7 +506,13 @@ class EmbeddingPlanner(object):
         if fast_slots:
             x = bufs["main"].data
             self.route = None
-            if getattr(self, "sharded", False):
+            peer = None
+            if getattr(self, "sharded", False) and getattr(self, "peer_mode", False):
+                # row-sharded tables addressed in place over NVLink peer mappings: same launch as one GPU
+                peer = self._peer_tables(fast_slots, self.fast and self.lin_hint and self._lin_matches_fast())
+                feats = [self._feature(s, feed, x, self.main_ld) for s in fast_slots]
+                lin_tabs = None
+            elif getattr(self, "sharded", False):
                 # ids -> owners (all-to-all), rows -> back (all-to-all); the returned row buffer then plays
                 # the role of the table and `pos` the role of the ids for the ordinary fused gather
                 id_feats = [self._feature(s, feed, x, self.main_ld) for s in fast_slots]
@@ -524,6 +548,8 @@ class EmbeddingPlanner(object):
                         fm_mask |= 1 << f
             plan = K.UniformPlan(feats, lin_tabs, dense, x, linear, fm, fm_mask)
             plan.g.x_cols = self.main_ld if only_fast else self.fast_n * fast_slots[0].dim
+            if peer is not None:
+                plan.set_peers(self.dist.world, peer[0].table, peer[1].table if peer[1] is not None else None)
             K.embed_gather_uniform_fwd(plan, batch)
             if fm is not None:
                 self.fm_result = (self.fm_hint, E.Var(fm.reshape(batch, 1)))
@@ -620,6 +646,23 @@ class EmbeddingPlanner(object):
                 lr = opt["optimizer"].lr if opt and opt.get("optimizer") else 0.0
                 sc = -lr / self.dist.world
                 self.exchange.push(st, tabs, ltabs, dimf, grows, glin, sc, sc)
+            elif (dx is not None or dfm is not None or dlin is not None) and plan.g.world > 1:
+                # peer mode: every rank applies its gradient rows at the owners (red.add over NVLink) with
+                # scale -lr / world (global-batch mean).  The all-reduce below separates the gathers of ALL
+                # ranks from the first update; the dense-gradient all-reduce at the end of the step separates
+                # the updates from the next step's gathers.
+                from . import parallel
+                emb, lin, token = self.peers
+                parallel.device_barrier(self.dist, token)
+                lr = opt["optimizer"].lr if opt and opt.get("optimizer") else 0.0
+                sc = -lr / self.dist.world
+                feats = [self._feature(s, feed, main.data, self.main_ld) for s in fast_slots]
+                bplan = K.UniformPlan(feats, None, None, main.data, None, None, plan.g.fm_mask[0])
+                bplan.g.x_cols = plan.g.x_cols
+                bplan.set_peers(self.dist.world, emb.table, lin.table if (lin is not None and lin_fused) else None)
+                K.embed_scatter_uniform_bwd(bplan, dx, None if dfm is None else dfm.reshape(-1).contiguous(),
+                                            None if dlin is None else dlin.reshape(-1).contiguous(),
+                                            sc, sc, batch)
             elif dx is not None or dfm is not None or dlin is not None:
                 tgts = [self._target(s.emb.embeddings, opt) for s in fast_slots]
                 feats = [self._feature(s, feed, main.data, self.main_ld, table=tgt)

@@ -120,6 +120,13 @@ class UniformPlan(object):
         self.g.fm_mask[0] = fm_mask & 0xFFFFFFFFFFFFFFFF
         self.g.fm_mask[1] = 0
 
+    def set_peers(self, world, peer_tables, peer_lin_tables):
+        """Row-sharded tables addressed through peer mappings (parallel.PeerTables.table device arrays)."""
+        self.peer_refs = (peer_tables, peer_lin_tables)
+        self.g.world = world
+        self.g.peer_tables = peer_tables.data_ptr()
+        self.g.peer_lin_tables = peer_lin_tables.data_ptr() if peer_lin_tables is not None else None
+
 
 def embed_gather_uniform_fwd(plan, batch):
     L.check(L.lib().b2ctr_embed_gather_uniform_fwd(C.byref(plan.g), batch, stream()),

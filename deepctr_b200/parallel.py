@@ -3,9 +3,16 @@
 * dense part (FM / CIN / Cross / attention / DNN / logit): data parallel - weights replicated, gradients
   averaged with ONE all-reduce over a flat bucket (`reduce_dense_grads`);
 * embedding tables of the fused fast path: ROW-SHARDED - row r of every table (and of its dim-1 linear
-  twin) lives on rank r % G as local row r // G; per step the lookups travel to their owners and the rows
-  travel back with two all-to-alls (ids, rows), the gradient rows return with a third, and the owner
-  applies them with the fused SGD scatter.  No collective is issued on a single GPU.
+  twin) lives on rank r % G as local row r // G.  Two transports:
+    - 'peer' (default on one NVSwitch box, world a power of two): every rank maps every other rank's shards
+      through CUDA IPC (`PeerTables`) and the ordinary fused gather / scatter kernels address the owner's
+      shard directly - rows are read with NVLink peer loads, gradient rows are applied with red.add at the
+      owner's L2.  No bucketing, no staging buffers, no host synchronisation; the only collective on the
+      embedding path is a tiny all-reduce that separates "everyone has gathered" from "anyone scatters".
+    - 'a2a' (fallback; B2CTR_SHARD_MODE=a2a): the lookups travel to their owners and the rows travel back
+      with NCCL all-to-alls (ids, rows), the gradient rows return with a third, and the owner applies them
+      with the fused SGD scatter (`ShardedExchange`).
+  No collective is issued on a single GPU.
 
 The reference has none of this (no sharding, no collectives: SURVEY.md section 2.1).
 
@@ -25,6 +32,56 @@ class DistContext(object):
         self.rank = dist.get_rank(group)
         self.world = dist.get_world_size(group)
         self.backend = dist.get_backend(group)
+
+
+class PeerTables(object):
+    """Device arrays of shard pointers [n_tables * world] (entry t * world + g = rank g's shard of table t)
+    for the b2ctr_uniform_gather_t.peer_tables / peer_lin_tables fields.  Peer shards are opened through
+    torch's CUDA-IPC storage sharing (cudaIpcOpenMemHandle underneath); the mapped tensors are kept alive
+    here, the owners keep their shards alive as model weights."""
+
+    def __init__(self, ctx, shards, lib):
+        import os
+        self.ctx = ctx
+        dev = shards[0].device
+        metas = []
+        for t in shards:
+            assert t.is_cuda and t.is_contiguous() and t.dtype == torch.float32
+            metas.append((t.untyped_storage()._share_cuda_(), t.storage_offset(), tuple(t.shape)))
+        every = [None] * ctx.world
+        dist.all_gather_object(every, (dev.index, metas), group=ctx.group)
+        self.mapped = []          # keeps the IPC mappings alive
+        ptrs = []
+        for t_i, own in enumerate(shards):
+            for g in range(ctx.world):
+                if g == ctx.rank:
+                    ptrs.append(own.data_ptr())
+                    continue
+                peer_dev, peer_metas = every[g]
+                handle, offset, shape = peer_metas[t_i]
+                if peer_dev != dev.index:
+                    lib.check(lib.lib().b2ctr_enable_peer_access(peer_dev), "enable_peer_access")
+                storage = torch.UntypedStorage._new_shared_cuda(*handle)
+                view = torch.empty(0, dtype=torch.float32, device=storage.device).set_(
+                    storage, offset, shape, _contig_strides(shape))
+                self.mapped.append(view)
+                ptrs.append(view.data_ptr())
+        self.table = torch.tensor(ptrs, dtype=torch.int64, device=dev)
+        dist.barrier(group=ctx.group)     # nobody proceeds (or frees) before every rank has mapped everything
+
+
+def _contig_strides(shape):
+    out, acc = [], 1
+    for s_ in reversed(shape):
+        out.append(acc)
+        acc *= s_
+    return tuple(reversed(out))
+
+
+def device_barrier(ctx, token):
+    """Stream-ordered cross-rank barrier: a 4-byte all-reduce completes only when every rank has reached it
+    on its stream (no host synchronisation)."""
+    dist.all_reduce(token, group=ctx.group)
 
 
 def shard_rows(full, rank, world):

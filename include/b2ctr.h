@@ -52,6 +52,10 @@ B2CTR_API void b2ctr_reset_launch_count(void);
  * persistent pool of `threads` helper threads (0 = pick from the core count, 1 = inline memcpy).  Replaces the
  * per-feature numpy -> tensor conversion of Keras' data adapter behind model.fit(model_input, y)
  * (reference examples/run_classification_criteo.py:48); the caller uploads dst with one cudaMemcpyAsync. */
+/* One process per GPU: let kernels of the current device dereference memory of `peer_device` that was
+ * mapped through CUDA IPC (cudaDeviceEnablePeerAccess; already-enabled is not an error). */
+B2CTR_API b2ctr_status_t b2ctr_enable_peer_access(int32_t peer_device);
+
 B2CTR_API b2ctr_status_t b2ctr_host_pack(const void* const* src, const int64_t* nbytes, const int64_t* dst_off,
                                          int32_t n, void* dst, int32_t threads);
 
@@ -136,7 +140,13 @@ typedef struct b2ctr_uniform_gather {
   int32_t ndense;
   uint64_t fm_mask[2];
   int32_t flags;                /* B2CTR_UNIFORM_* */
-  int32_t reserved;
+  int32_t world;                /* row shards per table (power of two); 0 / 1 = tables are whole         */
+  /* world > 1 (row-sharded tables read / updated IN PLACE over NVLink peer mappings, one process per GPU):
+   * row r of feature f lives at peer_tables[f * world + (r % world)] + (r / world) * dim.  Both arrays are
+   * DEVICE arrays of device pointers (the owner's own shard included); feats[f].table / lin_tables are then
+   * ignored.  Gathers are plain peer loads, the backward update is red.add at the owner's L2. */
+  float* const* peer_tables;
+  float* const* peer_lin_tables; /* [nfeat * world] or NULL */
 } b2ctr_uniform_gather_t;
 /* scatter_uniform_bwd: every (sample, feature) id is distinct (the ids are positions in a private row
  * buffer, as on the row-sharded path): write scale*g instead of accumulating, no zero-fill needed. */

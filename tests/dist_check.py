@@ -37,7 +37,7 @@ def main():
         _, x, y = H.criteo_like(rr, n, n_sparse=5, n_dense=3, vocab=37, dim=8)
         batches.append((x, y))
     x, y = batches[rank]
-    for step in range(3):
+    for step in range(6):     # steps >= 2 replay the captured step graph (peer mode)
         # forward parity on the local batch against the oracle with the FULL tables
         _, want = OM.deepfm(x, cols, cols, full)
         got = model.predict(x, batch_size=n)
@@ -70,7 +70,9 @@ def main():
             assert e < 3e-3, (rank, step, name, e)
     dist.barrier()
     if rank == 0:
-        print("dist_check OK: world %d, sharded tables + DP dense match the global-batch oracle" % world)
+        mode = "peer" if getattr(model.planner, "peer_mode", False) else "a2a"
+        print("dist_check OK: world %d, mode %s, step graphs %d, sharded tables + DP dense match the global-batch "
+              "oracle" % (world, mode, len(model._step_graphs)))
     dist.destroy_process_group()
 
 

@@ -61,7 +61,9 @@ class PeerTables(object):
                 handle, offset, shape = peer_metas[t_i]
                 if peer_dev != dev.index:
                     lib.check(lib.lib().b2ctr_enable_peer_access(peer_dev), "enable_peer_access")
-                storage = torch.UntypedStorage._new_shared_cuda(*handle)
+                # open the handle with THIS rank's device current (first tuple element): the runtime then maps
+                # the owner's memory into this device's address space (cudaIpcMemLazyEnablePeerAccess)
+                storage = torch.UntypedStorage._new_shared_cuda(dev.index, *handle[1:])
                 view = torch.empty(0, dtype=torch.float32, device=storage.device).set_(
                     storage, offset, shape, _contig_strides(shape))
                 self.mapped.append(view)

@@ -327,10 +327,12 @@ def main():
     h2d = model._feeder.h2d_bytes // args.steps
     d2h = model.d2h_bytes // args.steps
 
+    if world > 1:
+        model.close()          # step graphs hold NCCL kernels, the planner holds IPC mappings of peer shards
+        dist.barrier()
     if rank != 0:
-        if world > 1:
-            dist.destroy_process_group()
-        return
+        sys.stdout.flush()
+        os._exit(0)
 
     peaks = measured_peaks()
     F, E, nd, B = cfg["n_sparse"], cfg["dim"], cfg["n_dense"], cfg["batch"]
@@ -392,8 +394,9 @@ def main():
             "roofline_gemm": roof_gemm, "kernel_ms_per_step": kernels, "shares": shares,
             "cpu_baseline": cpu}
     print(json.dumps(line))
+    sys.stdout.flush()
     if world > 1:
-        dist.destroy_process_group()
+        os._exit(0)            # all ranks passed the barrier above; skip collective teardown at exit
 
 
 if __name__ == "__main__":

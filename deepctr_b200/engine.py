@@ -945,6 +945,23 @@ class Model(object):
         for w in self.weights:
             w.materialize()
 
+    def close(self):
+        """Release what must not outlive the process group: captured step graphs (they hold NCCL kernels) and
+        the CUDA-IPC mappings of the other ranks' table shards.  Call before dist.destroy_process_group()."""
+        import gc
+        self._step_graphs = {}
+        self._graph_pool = None
+        planner = getattr(self, "planner", None)
+        if planner is not None and getattr(planner, "peers", None) is not None:
+            for pt in planner.peers[:2]:
+                if pt is not None:
+                    pt.close()
+            planner.peers = None
+        gc.collect()
+        if torch.cuda.is_available():
+            torch.cuda.synchronize()
+            torch.cuda.ipc_collect()
+
     def _run(self, feed, training, upto=None):
         """Execute the graph; returns {id(KTensor): Var}.  ``upto``: stop before this node."""
         values = {}

@@ -71,6 +71,10 @@ class PeerTables(object):
         self.table = torch.tensor(ptrs, dtype=torch.int64, device=dev)
         dist.barrier(group=ctx.group)     # nobody proceeds (or frees) before every rank has mapped everything
 
+    def close(self):
+        self.mapped = []
+        self.table = None
+
 
 def _contig_strides(shape):
     out, acc = [], 1

@@ -382,7 +382,9 @@ def main():
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
             "data": "synthetic",
             "config": {"workload": cfg["workload"], "global_batch": world * B, "optimizer": "sgd (fused row-wise)",
-                       "gemm_precision": precision, "parallelism": "replicas x%d" % world if world > 1 else "1 gpu",
+                       "gemm_precision": precision, "parallelism": ("tables row-sharded over %d GPUs (%s), dense part data-parallel" %
+                                       (world, "NVLink peer loads / red.add" if getattr(model.planner, "peer_mode", False)
+                                        else "NCCL all-to-all")) if world > 1 else "1 gpu",
                        "l2_flush": "none: %d distinct batches cycle; per step the path touches %.1f GB of "
                                    "randomly addressed table rows + activations, >> 126 MB L2"
                                    % (N_BATCHES, (gather_fwd_bytes + scatter_bwd_bytes) * B / 1e9)},

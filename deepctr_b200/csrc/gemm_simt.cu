@@ -141,6 +141,100 @@ __global__ void splitk_reduce_kernel(const GemmArgs g) {
   }
 }
 
+
+// ---- skinny shapes -----------------------------------------------------------------------------
+// The final [*, 1] projection of every CTR tower (and its dgrad) is a GEMV / outer product: HBM-bound, and a
+// 128 x 32 tile kernel spends 97 % of its lanes on padding (measured 81 us for M = 65536, K = 64, N = 1).
+//
+// N <= 8, A row-major: LPR lanes share a row (float4 each per pass), partial dot products meet by shuffles.
+template <int N>
+__global__ void __launch_bounds__(256) skinny_n_kernel(const GemmArgs g, int lpr, int vec) {
+  const int lane = threadIdx.x & 31;
+  const int rows_per_warp = 32 / lpr;
+  const int sub = lane / lpr, li = lane % lpr;
+  const int64_t warp = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+  for (int64_t r0 = warp * rows_per_warp; r0 < g.m; r0 += nwarps * rows_per_warp) {
+    const int64_t r = r0 + sub;
+    float acc[N];
+#pragma unroll
+    for (int n = 0; n < N; ++n) acc[n] = 0.f;
+    if (r < g.m) {
+      const float* arow = g.a + r * g.sam;
+      if (vec) {
+        for (int64_t k = (int64_t)li * 4; k < g.k; k += (int64_t)lpr * 4) {
+          const float4 a = __ldg(reinterpret_cast<const float4*>(arow + k));
+#pragma unroll
+          for (int n = 0; n < N; ++n) {
+            if (n < g.n) {
+              const float* bp = g.b + k * g.sbk + n * g.sbn;
+              acc[n] = fmaf(a.x, __ldg(bp), acc[n]);
+              if (k + 1 < g.k) acc[n] = fmaf(a.y, __ldg(bp + g.sbk), acc[n]);
+              if (k + 2 < g.k) acc[n] = fmaf(a.z, __ldg(bp + 2 * g.sbk), acc[n]);
+              if (k + 3 < g.k) acc[n] = fmaf(a.w, __ldg(bp + 3 * g.sbk), acc[n]);
+            }
+          }
+        }
+      } else {
+        for (int64_t k = li; k < g.k; k += lpr) {
+          const float a = __ldg(arow + k);
+#pragma unroll
+          for (int n = 0; n < N; ++n)
+            if (n < g.n) acc[n] = fmaf(a, __ldg(g.b + k * g.sbk + n * g.sbn), acc[n]);
+        }
+      }
+    }
+#pragma unroll
+    for (int n = 0; n < N; ++n)
+      for (int o = lpr >> 1; o > 0; o >>= 1) acc[n] += __shfl_xor_sync(0xffffffffu, acc[n], o);
+    if (r < g.m && li == 0) {
+#pragma unroll
+      for (int n = 0; n < N; ++n) {
+        if (n < g.n) {
+          float v = g.alpha * acc[n];
+          if (g.accumulate) v += g.c[r * g.ldc + n];
+          if (g.bias) v += g.bias[n];
+          g.c[r * g.ldc + n] = act_apply(v, g.act);
+        }
+      }
+    }
+  }
+}
+// K <= 8, A row-major: C[m, n] = sum_k A[m,k] B(k,n) is an outer-product-shaped stream of writes
+// (dgrad of a [*, 1] layer); thread = (row, 4 consecutive columns).
+__global__ void __launch_bounds__(256) skinny_k_kernel(const GemmArgs g, int vec_c) {
+  const int64_t chunks = (g.n + 3) / 4;
+  const int64_t total = g.m * chunks;
+  for (int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; t < total; t += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t r = t / chunks;
+    const int64_t n0 = (t - r * chunks) * 4;
+    float v[4] = {0.f, 0.f, 0.f, 0.f};
+    for (int k = 0; k < g.k; ++k) {
+      const float a = __ldg(g.a + r * g.sam + k);
+#pragma unroll
+      for (int j = 0; j < 4; ++j)
+        if (n0 + j < g.n) v[j] = fmaf(a, __ldg(g.b + k * g.sbk + (n0 + j) * g.sbn), v[j]);
+    }
+    float* cp = g.c + r * g.ldc + n0;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      if (n0 + j < g.n) {
+        float o = g.alpha * v[j];
+        if (g.accumulate) o += cp[j];
+        if (g.bias) o += g.bias[n0 + j];
+        v[j] = act_apply(o, g.act);
+      }
+    }
+    if (vec_c && n0 + 4 <= g.n) {
+      *reinterpret_cast<float4*>(cp) = make_float4(v[0], v[1], v[2], v[3]);
+    } else {
+#pragma unroll
+      for (int j = 0; j < 4; ++j)
+        if (n0 + j < g.n) cp[j] = v[j];
+    }
+  }
+}
+
 template <int BM, int BN>
 static void launch_cfg(const GemmArgs& ga, bool akc, bool bnc, cudaStream_t st) {
   dim3 grid((unsigned)ceil_div(ga.n, BN), (unsigned)ceil_div(ga.m, BM), (unsigned)ga.splits);
@@ -168,6 +262,24 @@ b2ctr_status_t gemm_fp32(const b2ctr_gemm_t* g, void* workspace, size_t workspac
   }
   ga.k_per_split = ceil_div(ceil_div(g->k, ga.splits), kBK) * kBK;
   const bool akc = !g->trans_a, bnc = !g->trans_b;
+  if (akc && ga.splits == 1 && g->n <= 8 && g->k >= 16) {
+    int lpr = 1;
+    while (lpr < 32 && lpr * 4 < g->k) lpr <<= 1;
+    const int vec = (g->lda % 4 == 0) && ((reinterpret_cast<uintptr_t>(g->a) & 15) == 0);
+    const int grid = grid_for(ceil_div(g->m, 32 / lpr), 8, 8);
+    if (g->n <= 1) skinny_n_kernel<1><<<grid, 256, 0, st>>>(ga, lpr, vec);
+    else if (g->n <= 2) skinny_n_kernel<2><<<grid, 256, 0, st>>>(ga, lpr, vec);
+    else if (g->n <= 4) skinny_n_kernel<4><<<grid, 256, 0, st>>>(ga, lpr, vec);
+    else skinny_n_kernel<8><<<grid, 256, 0, st>>>(ga, lpr, vec);
+    B2_CHECK_LAUNCH("b2ctr_gemm(fp32 skinny-N)");
+    return B2CTR_OK;
+  }
+  if (akc && ga.splits == 1 && g->k <= 8 && g->n >= 16) {
+    const int vec_c = (g->ldc % 4 == 0) && ((reinterpret_cast<uintptr_t>(g->c) & 15) == 0);
+    skinny_k_kernel<<<grid_for(g->m * ceil_div(g->n, 4), 256, 8), 256, 0, st>>>(ga, vec_c);
+    B2_CHECK_LAUNCH("b2ctr_gemm(fp32 skinny-K)");
+    return B2CTR_OK;
+  }
   if (g->n <= 32) launch_cfg<128, 32>(ga, akc, bnc, st);
   else if (g->n <= 64) launch_cfg<128, 64>(ga, akc, bnc, st);
   else launch_cfg<128, 128>(ga, akc, bnc, st);

@@ -31,6 +31,30 @@ def test_gemm_fp32_layouts(cuda, m, n, k, ta, tb):
     torch.testing.assert_close(got.cpu(), want, rtol=1e-4, atol=1e-4)
 
 
+@pytest.mark.parametrize("m,n,k", [(5000, 3, 70), (4096, 8, 64), (3000, 5, 16), (2049, 64, 1), (1000, 17, 8),
+                                   (65536, 1, 64), (777, 2, 1000), (33, 1, 19)])
+@pytest.mark.parametrize("tb", [False, True])
+def test_gemm_fp32_skinny_shapes(cuda, m, n, k, tb):
+    """GEMV (N <= 8) and outer-product (K <= 8) kernels behind the same b2ctr_gemm entry point: the last
+    [*, 1] projection of every tower and its dgrad; strided A / C, alpha, accumulate, bias + activation."""
+    K, L = _kern()
+    rng = np.random.RandomState(m + n + k)
+    a_wide = _r(rng, m, k + 4).to(cuda)
+    a = a_wide[:, :k]                                   # lda = k + 4
+    b = _r(rng, *((n, k) if tb else (k, n))).to(cuda)
+    bias = _r(rng, n).to(cuda)
+    A, Bm = a.cpu().double(), (b.t() if tb else b).cpu().double()
+    got = K.gemm(a, b, bias=bias, trans_b=tb, act=L.ACT_TANH, m=m, n=n, k=k)
+    want = torch.tanh(A @ Bm + bias.cpu().double()).float()
+    torch.testing.assert_close(got.cpu(), want, rtol=1e-4, atol=1e-4)
+    c_wide = _r(rng, m, n + 3).to(cuda)
+    c0 = c_wide.clone()
+    K.gemm(a, b, c=c_wide[:, :n], trans_b=tb, accumulate=True, alpha=0.25, m=m, n=n, k=k)
+    want2 = c0.cpu().double()
+    want2[:, :n] += 0.25 * (A @ Bm)
+    torch.testing.assert_close(c_wide.cpu(), want2.float(), rtol=1e-4, atol=1e-4)   # columns >= n untouched
+
+
 def test_gemm_splitk_accumulate_and_ld(cuda):
     K, L = _kern()
     rng = np.random.RandomState(3)

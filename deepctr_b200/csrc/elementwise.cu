@@ -81,21 +81,23 @@ __global__ void __launch_bounds__(256)
     }
   }
 }
-// one block per 32 columns; 8 warps stride the partial blocks, combined in a fixed order
+// one block per 8 columns; 32 row-lanes stride the partial blocks and meet in shared memory in a fixed order
+// (deterministic).  8-column blocks keep >= 32 CTAs busy at n = 256 - with 32-column blocks the reduce of a
+// 512-row partial matrix ran on 8 CTAs and cost 12 us per layer.
 __global__ void __launch_bounds__(256)
     bias_reduce_kernel(const float* __restrict__ partial, float* dbias, int64_t nblocks, int64_t n) {
-  __shared__ float red[8][33];
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  const int64_t c = (int64_t)blockIdx.x * 32 + lane;
+  __shared__ float red[32][9];
+  const int col = threadIdx.x & 7, rl = threadIdx.x >> 3;
+  const int64_t c = (int64_t)blockIdx.x * 8 + col;
   float s = 0.f;
   if (c < n)
-    for (int64_t b = warp; b < nblocks; b += 8) s += partial[b * n + c];
-  red[warp][lane] = s;
+    for (int64_t b = rl; b < nblocks; b += 32) s += partial[b * n + c];
+  red[rl][col] = s;
   __syncthreads();
-  if (warp == 0 && c < n) {
+  if (rl == 0 && c < n) {
     float t = 0.f;
 #pragma unroll
-    for (int w = 0; w < 8; ++w) t += red[w][lane];
+    for (int w = 0; w < 32; ++w) t += red[w][col];
     dbias[c] = t;
   }
 }
@@ -360,7 +362,7 @@ b2ctr_status_t b2ctr_bias_act_bwd(const float* dy, const float* y, float* dz, fl
                                                           m, n, ld, act);
   B2_CHECK_LAUNCH("b2ctr_bias_act_bwd");
   if (dbias) {
-    bias_reduce_kernel<<<(unsigned)ceil_div(n, 32), 256, 0, ST>>>((const float*)workspace, dbias,
+    bias_reduce_kernel<<<(unsigned)ceil_div(n, 8), 256, 0, ST>>>((const float*)workspace, dbias,
                                                                  nblocks, n);
     B2_CHECK_LAUNCH("b2ctr_bias_act_bwd(reduce)");
   }

@@ -200,6 +200,57 @@ __global__ void __launch_bounds__(256) skinny_n_kernel(const GemmArgs g, int lpr
     }
   }
 }
+// A stored [K, M] (wgrad of a skinny layer: C[m, n] = sum_k A[k, m] B(k, n), N <= 8, K = batch): a stream over
+// the rows of A; thread = (column m, one of 4 k-lanes), 8 independent row loads in flight, k-lanes meet in
+// shared memory.  One CTA per (64-column block, K slice); slices go through the split-K workspace.
+template <int N>
+__global__ void __launch_bounds__(256) skinny_tn_kernel(const GemmArgs g) {
+  __shared__ float red[4][64][N];
+  const int col = threadIdx.x & 63, kl = threadIdx.x >> 6;
+  const int64_t m = (int64_t)blockIdx.x * 64 + col;
+  const int64_t kbeg = (int64_t)blockIdx.z * g.k_per_split;
+  const int64_t kend = kbeg + g.k_per_split < g.k ? kbeg + g.k_per_split : g.k;
+  float acc[N];
+#pragma unroll
+  for (int n = 0; n < N; ++n) acc[n] = 0.f;
+  if (m < g.m) {
+    int64_t k = kbeg + kl;
+    for (; k + 28 < kend; k += 32) {
+      float a[8];
+#pragma unroll
+      for (int u = 0; u < 8; ++u) a[u] = __ldg(g.a + (k + 4 * u) * g.sak + m);
+#pragma unroll
+      for (int u = 0; u < 8; ++u)
+#pragma unroll
+        for (int n = 0; n < N; ++n)
+          if (n < g.n) acc[n] = fmaf(a[u], __ldg(g.b + (k + 4 * u) * g.sbk + n * g.sbn), acc[n]);
+    }
+    for (; k < kend; k += 4) {
+      const float a = __ldg(g.a + k * g.sak + m);
+#pragma unroll
+      for (int n = 0; n < N; ++n)
+        if (n < g.n) acc[n] = fmaf(a, __ldg(g.b + k * g.sbk + n * g.sbn), acc[n]);
+    }
+  }
+#pragma unroll
+  for (int n = 0; n < N; ++n) red[kl][col][n] = acc[n];
+  __syncthreads();
+  if (kl == 0 && m < g.m) {
+#pragma unroll
+    for (int n = 0; n < N; ++n) {
+      if (n < g.n) {
+        float v = g.alpha * (((red[0][col][n] + red[1][col][n]) + red[2][col][n]) + red[3][col][n]);
+        if (g.splits > 1) {
+          g.ws[((int64_t)blockIdx.z * g.m + m) * g.n + n] = v;
+        } else {
+          if (g.accumulate) v += g.c[m * g.ldc + n];
+          if (g.bias) v += g.bias[n];
+          g.c[m * g.ldc + n] = act_apply(v, g.act);
+        }
+      }
+    }
+  }
+}
 // K <= 8, A row-major: C[m, n] = sum_k A[m,k] B(k,n) is an outer-product-shaped stream of writes
 // (dgrad of a [*, 1] layer); thread = (row, 4 consecutive columns).
 __global__ void __launch_bounds__(256) skinny_k_kernel(const GemmArgs g, int vec_c) {
@@ -272,6 +323,20 @@ b2ctr_status_t gemm_fp32(const b2ctr_gemm_t* g, void* workspace, size_t workspac
     else if (g->n <= 4) skinny_n_kernel<4><<<grid, 256, 0, st>>>(ga, lpr, vec);
     else skinny_n_kernel<8><<<grid, 256, 0, st>>>(ga, lpr, vec);
     B2_CHECK_LAUNCH("b2ctr_gemm(fp32 skinny-N)");
+    return B2CTR_OK;
+  }
+  if (!akc && g->n <= 8 && g->k >= 64) {
+    // sak = lda (A stored [K, M]); the K slices of split-K launches land in the workspace as usual
+    dim3 grid((unsigned)ceil_div(g->m, 64), 1, (unsigned)ga.splits);
+    if (g->n <= 1) skinny_tn_kernel<1><<<grid, 256, 0, st>>>(ga);
+    else if (g->n <= 2) skinny_tn_kernel<2><<<grid, 256, 0, st>>>(ga);
+    else if (g->n <= 4) skinny_tn_kernel<4><<<grid, 256, 0, st>>>(ga);
+    else skinny_tn_kernel<8><<<grid, 256, 0, st>>>(ga);
+    B2_CHECK_LAUNCH("b2ctr_gemm(fp32 skinny-TN)");
+    if (ga.splits > 1) {
+      splitk_reduce_kernel<<<grid_for(g->m * g->n, 256, 4), 256, 0, st>>>(ga);
+      B2_CHECK_LAUNCH("b2ctr_gemm(splitk_reduce)");
+    }
     return B2CTR_OK;
   }
   if (akc && ga.splits == 1 && g->k <= 8 && g->n >= 16) {

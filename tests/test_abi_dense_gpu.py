@@ -55,6 +55,24 @@ def test_gemm_fp32_skinny_shapes(cuda, m, n, k, tb):
     torch.testing.assert_close(c_wide.cpu(), want2.float(), rtol=1e-4, atol=1e-4)   # columns >= n untouched
 
 
+@pytest.mark.parametrize("m,n,k,sk", [(64, 1, 65536, 74), (13, 1, 65536, 74), (845, 3, 9000, 4), (64, 1, 200, 1),
+                                      (100, 8, 4097, 5), (1, 1, 70000, 64)])
+@pytest.mark.parametrize("tb", [False, True])
+def test_gemm_fp32_skinny_wgrad(cuda, m, n, k, sk, tb):
+    """A stored [K, M] with N <= 8 (wgrad of the [*, 1] projections): streaming reduction over the batch,
+    K slices through the split-K workspace."""
+    K, L = _kern()
+    rng = np.random.RandomState(m + n + k)
+    a_wide = _r(rng, k, m + 4).to(cuda)
+    a = a_wide[:, :m]
+    b = _r(rng, *((n, k) if tb else (k, n))).to(cuda)
+    c0 = _r(rng, m, n)
+    want = c0.double() + 0.5 * (a.cpu().double().t() @ (b.t() if tb else b).cpu().double())
+    c = c0.to(cuda)
+    K.gemm(a, b, c=c, trans_a=True, trans_b=tb, accumulate=True, alpha=0.5, split_k=sk, m=m, n=n, k=k)
+    torch.testing.assert_close(c.cpu(), want.float(), rtol=1e-4, atol=2e-3 * max(1.0, (k / 256.0) ** 0.5))
+
+
 def test_gemm_splitk_accumulate_and_ld(cuda):
     K, L = _kern()
     rng = np.random.RandomState(3)

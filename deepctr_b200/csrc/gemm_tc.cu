@@ -748,7 +748,7 @@ __global__ void __launch_bounds__(kWsThreads, 1) gemm_planes_ws_kernel(const __g
   extern __shared__ unsigned char smem_raw[];
   unsigned char* tiles = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) &
                                                           ~(uintptr_t)1023);
-  __shared__ __align__(8) uint64_t full_bar[STAGES], empty_bar[STAGES], acc_full[2], acc_empty[2];
+  __shared__ __align__(8) uint64_t full_bar[STAGES], peer_full[STAGES], empty_bar[STAGES], acc_full[2], acc_empty[2];
   __shared__ uint32_t tmem_slot;
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -757,7 +757,8 @@ __global__ void __launch_bounds__(kWsThreads, 1) gemm_planes_ws_kernel(const __g
 
   if (threadIdx.x == 0) {
     for (int s = 0; s < STAGES; ++s) {
-      mbar_init(&full_bar[s], kWsProducers * NCTA);   // used on the leader only
+      mbar_init(&full_bar[s], kWsProducers * 32);     // one deferred arrival per producer thread of THIS CTA
+      mbar_init(&peer_full[s], 1);                    // leader only: the peer CTA's half of the stage landed
       mbar_init(&empty_bar[s], 1);
     }
     for (int a = 0; a < 2; ++a) {
@@ -808,73 +809,60 @@ __global__ void __launch_bounds__(kWsThreads, 1) gemm_planes_ws_kernel(const __g
       if (nkb > 0) break;
       tile += nclusters;
     }
-    uint32_t issued = 0, published = 0;
-    for (uint32_t it = 0; tile < w.ntiles || published < issued; ++it) {
-      // (1) publish the block issued STAGES-1 iterations ago BEFORE blocking on a free stage: the MMA issuer
-      //     then always has the next block ready while this warp waits for the oldest stage to drain
-      if (it >= STAGES - 1 && published < issued) {
-        asm volatile("cp.async.wait_group %0;" ::"n"(STAGES - 2) : "memory");
-        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic-proxy writes -> tensor core
-        __syncwarp();
-        if (lane == 0) {
-          if (NCTA == 1 || cta_rank == 0) mbar_arrive(&full_bar[published % STAGES]);
-          else mbar_arrive_cluster(&full_bar[published % STAGES], 0);
+    // Every producer thread hands its copies to the stage's mbarrier (cp.async.mbarrier.arrive.noinc: the
+    // arrival fires when the thread's cp.asyncs have landed), so this warp never waits for data - only for a
+    // free stage - and all STAGES blocks are genuinely in flight.
+    for (uint32_t it = 0; tile < w.ntiles; ++it) {
+      const int s = it % STAGES;
+      mbar_wait(&empty_bar[s], ((it / STAGES) & 1) ^ 1);
+      const uint32_t st = smem_u32(tiles + (size_t)s * STAGE);
+      const int64_t k0 = kbeg + (int64_t)kb * kTK;
+      const int64_t m0 = (mt * NCTA + cta_rank) * kTM;
+      const int64_t n0 = nt * BN + (int64_t)cta_rank * BNH;
+#pragma unroll 4
+      for (int t = tid; t < kTM * 8; t += NT) {
+        uint32_t off;
+        int64_t src;
+        if (g.a_mn) {
+          const int kk = t / (kTM / 8), c = t % (kTM / 8);
+          off = (c >> 3) * 8192 + kk * 128 + (((c & 7) ^ (kk & 7)) << 4);
+          src = (k0 + kk) * g.a_pitch + m0 + c * 8;
+        } else {
+          const int r = t >> 3, c = t & 7;
+          off = r * 128 + ((c ^ (r & 7)) << 4);
+          src = (m0 + r) * g.a_pitch + k0 + c * 8;
         }
-        ++published;
+        cp_async16(st + off, g.a_hi + src);
+        cp_async16(st + A_PLANE + off, g.a_lo + src);
       }
-      // (2) refill the stage the MMAs of block it-STAGES have drained
-      if (tile < w.ntiles) {
-        const int s = it % STAGES;
-        mbar_wait(&empty_bar[s], ((it / STAGES) & 1) ^ 1);
-        const uint32_t st = smem_u32(tiles + (size_t)s * STAGE);
-        const int64_t k0 = kbeg + (int64_t)kb * kTK;
-        const int64_t m0 = (mt * NCTA + cta_rank) * kTM;
-        const int64_t n0 = nt * BN + (int64_t)cta_rank * BNH;
 #pragma unroll 4
-        for (int t = tid; t < kTM * 8; t += NT) {
-          uint32_t off;
-          int64_t src;
-          if (g.a_mn) {
-            const int kk = t / (kTM / 8), c = t % (kTM / 8);
-            off = (c >> 3) * 8192 + kk * 128 + (((c & 7) ^ (kk & 7)) << 4);
-            src = (k0 + kk) * g.a_pitch + m0 + c * 8;
-          } else {
-            const int r = t >> 3, c = t & 7;
-            off = r * 128 + ((c ^ (r & 7)) << 4);
-            src = (m0 + r) * g.a_pitch + k0 + c * 8;
-          }
-          cp_async16(st + off, g.a_hi + src);
-          cp_async16(st + A_PLANE + off, g.a_lo + src);
+      for (int t = tid; t < BNH * 8; t += NT) {
+        uint32_t off;
+        int64_t src;
+        if (g.b_mn) {
+          const int kk = t / (BNH / 8), c = t % (BNH / 8);
+          off = (c >> 3) * 8192 + kk * 128 + (((c & 7) ^ (kk & 7)) << 4);
+          src = (k0 + kk) * g.b_pitch + n0 + c * 8;
+        } else {
+          const int r = t >> 3, c = t & 7;
+          off = r * 128 + ((c ^ (r & 7)) << 4);
+          src = (n0 + r) * g.b_pitch + k0 + c * 8;
         }
-#pragma unroll 4
-        for (int t = tid; t < BNH * 8; t += NT) {
-          uint32_t off;
-          int64_t src;
-          if (g.b_mn) {
-            const int kk = t / (BNH / 8), c = t % (BNH / 8);
-            off = (c >> 3) * 8192 + kk * 128 + (((c & 7) ^ (kk & 7)) << 4);
-            src = (k0 + kk) * g.b_pitch + n0 + c * 8;
-          } else {
-            const int r = t >> 3, c = t & 7;
-            off = r * 128 + ((c ^ (r & 7)) << 4);
-            src = (n0 + r) * g.b_pitch + k0 + c * 8;
-          }
-          cp_async16(st + 2 * A_PLANE + off, g.b_hi + src);
-          cp_async16(st + 2 * A_PLANE + B_PLANE + off, g.b_lo + src);
-        }
-        ++issued;
-        if (++kb == nkb) {               // next tile with work
-          kb = 0;
+        cp_async16(st + 2 * A_PLANE + off, g.b_hi + src);
+        cp_async16(st + 2 * A_PLANE + B_PLANE + off, g.b_lo + src);
+      }
+      asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];" ::"r"(smem_u32(&full_bar[s])) : "memory");
+      if (++kb == nkb) {               // next tile with work
+        kb = 0;
+        tile += nclusters;
+        while (tile < w.ntiles) {
+          decode(tile, mt, nt, kbeg, nkb);
+          if (nkb > 0) break;
           tile += nclusters;
-          while (tile < w.ntiles) {
-            decode(tile, mt, nt, kbeg, nkb);
-            if (nkb > 0) break;
-            tile += nclusters;
-          }
         }
       }
-      asm volatile("cp.async.commit_group;" ::: "memory");
     }
+    asm volatile("cp.async.wait_all;" ::: "memory");
   } else if (warp == kMmaWarp) {
     // ------------------------------------------------------------------------------ MMA issuer
     if (cta_rank == 0) {
@@ -893,7 +881,8 @@ __global__ void __launch_bounds__(kWsThreads, 1) gemm_planes_ws_kernel(const __g
         const uint32_t tmem_d = tmem_base + ab * BN;
         for (int kb = 0; kb < nkb; ++kb, ++it) {
           const int s = it % STAGES;
-          mbar_wait_cluster(&full_bar[s], (it / STAGES) & 1);
+          mbar_wait(&full_bar[s], (it / STAGES) & 1);
+          if constexpr (NCTA > 1) mbar_wait_cluster(&peer_full[s], (it / STAGES) & 1);
           asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
           if (lane == 0) {
             const uint32_t sa = smem_u32(tiles + (size_t)s * STAGE);
@@ -912,6 +901,20 @@ __global__ void __launch_bounds__(kWsThreads, 1) gemm_planes_ws_kernel(const __g
           __syncwarp();
         }
         ++acc_it;
+      }
+    } else {
+      // peer CTA: relay "my half of stage s has landed" to the leader, which issues the MMAs of the pair
+      uint32_t it = 0;
+      for (int64_t tile = cluster_id; tile < w.ntiles; tile += nclusters) {
+        int64_t mt, nt, kbeg;
+        int nkb;
+        decode(tile, mt, nt, kbeg, nkb);
+        for (int kb = 0; kb < nkb; ++kb, ++it) {
+          const int s = it % STAGES;
+          mbar_wait(&full_bar[s], (it / STAGES) & 1);
+          if (lane == 0) mbar_arrive_cluster(&peer_full[s], 0);
+          __syncwarp();
+        }
       }
     }
   } else {

@@ -43,6 +43,10 @@ static inline int grid_for(int64_t work_items, int items_per_block, int blocks_p
   return (int)(need < cap ? need : cap);
 }
 
+// bf16 hi/lo operand planes of the split-bf16 GEMM (b2ctr_split_planes): padded extent of a [rows, cols] matrix
+static inline int64_t planes_rows_pad(int64_t rows) { return (rows + 255) / 256 * 256; }
+static inline int64_t planes_cols_pad(int64_t cols) { return cols <= 64 ? 64 : (cols + 127) / 128 * 128; }
+
 // ---- device helpers -------------------------------------------------------------------------
 #ifdef __CUDACC__
 

@@ -19,6 +19,17 @@ int32_t b2ctr_abi_version(void) { return 1; }
 const char* b2ctr_last_error(void) { return b2ctr::g_err; }
 int64_t b2ctr_launch_count(void) { return (int64_t)b2ctr::g_launches.load(); }
 void b2ctr_reset_launch_count(void) { b2ctr::g_launches.store(0); }
+b2ctr_status_t b2ctr_set_l2_fetch_granularity(int32_t bytes) {
+  // cudaLimitMaxL2FetchGranularity is a hint (32 / 64 / 128): with random 4-byte and 128-byte row reads the
+  // default 64 B granule doubles the DRAM traffic of every dim-1 (linear-term) lookup
+  cudaError_t e = cudaDeviceSetLimit(cudaLimitMaxL2FetchGranularity, (size_t)bytes);
+  if (e != cudaSuccess) {
+    b2ctr::set_error("set_l2_fetch_granularity(%d): %s", bytes, cudaGetErrorString(e));
+    cudaGetLastError();
+    return B2CTR_ERR_CUDA;
+  }
+  return B2CTR_OK;
+}
 b2ctr_status_t b2ctr_enable_peer_access(int32_t peer_device) {
   cudaError_t e = cudaDeviceEnablePeerAccess(peer_device, 0);
   if (e == cudaErrorPeerAccessAlreadyEnabled) {

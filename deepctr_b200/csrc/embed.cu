@@ -11,6 +11,7 @@
 //   * row updates are REDG.E.ADD.F32x4 (the add executes in the L2 slice, no read by the SM);
 //   * grids are whole multiples of 148 SMs.
 #include <stdlib.h>
+#include <cuda_bf16.h>
 #include "common.cuh"
 
 namespace b2ctr {
@@ -400,7 +401,28 @@ struct UniParams {
   float* const* peer_lin;
   int32_t world;
   int32_t wshift;
+  // optional bf16 hi/lo planes of x (first DNN GEMM operand): row pitch xp_pitch elements, columns
+  // [0, xp_pitch) are written (zero beyond the data)
+  __nv_bfloat16* xp_hi;
+  __nv_bfloat16* xp_lo;
+  int64_t xp_pitch;
 };
+
+__device__ __forceinline__ void store_planes4(const UniParams& p, int64_t off, float4 v) {
+  const __nv_bfloat16 h0 = __float2bfloat16_rn(v.x), h1 = __float2bfloat16_rn(v.y);
+  const __nv_bfloat16 h2 = __float2bfloat16_rn(v.z), h3 = __float2bfloat16_rn(v.w);
+  const __nv_bfloat16 l0 = __float2bfloat16_rn(v.x - __bfloat162float(h0));
+  const __nv_bfloat16 l1 = __float2bfloat16_rn(v.y - __bfloat162float(h1));
+  const __nv_bfloat16 l2 = __float2bfloat16_rn(v.z - __bfloat162float(h2));
+  const __nv_bfloat16 l3 = __float2bfloat16_rn(v.w - __bfloat162float(h3));
+  uint2 h, l;
+  h.x = (uint32_t)__bfloat16_as_ushort(h0) | ((uint32_t)__bfloat16_as_ushort(h1) << 16);
+  h.y = (uint32_t)__bfloat16_as_ushort(h2) | ((uint32_t)__bfloat16_as_ushort(h3) << 16);
+  l.x = (uint32_t)__bfloat16_as_ushort(l0) | ((uint32_t)__bfloat16_as_ushort(l1) << 16);
+  l.y = (uint32_t)__bfloat16_as_ushort(l2) | ((uint32_t)__bfloat16_as_ushort(l3) << 16);
+  *reinterpret_cast<uint2*>(p.xp_hi + off) = h;
+  *reinterpret_cast<uint2*>(p.xp_lo + off) = l;
+}
 
 // peer (NVLink) accesses: no read-only / L2-policy qualifiers - the line lives in the owner's L2
 __device__ __forceinline__ float4 ld_peer_f4(const float* p) {
@@ -437,8 +459,8 @@ __device__ __forceinline__ int64_t uni_id(const UniParams& p, int f, int64_t b) 
 // Latency hiding (ncu, profiles/r1_embed_before.txt: 40 % DRAM, 35 % warps active): the id -> row -> store
 // chain is broken by prefetching the NEXT sample's ids before the current rows are requested, and the
 // register budget is capped at 64 (4 CTAs = 32 warps per SM).
-template <int LPR, bool SHARD>
-__global__ void __launch_bounds__(256, SHARD ? 3 : 4)
+template <int LPR, bool SHARD, bool PLANES>
+__global__ void __launch_bounds__(256, (SHARD || PLANES) ? 3 : 4)
     gather_uniform_fwd_kernel(const __grid_constant__ UniParams p, int64_t batch) {
   constexpr int RPI = 32 / LPR;
   constexpr int U = 7;   // 7 x RPI(4) = 28 >= 26 Criteo fields in one pass at dim 32
@@ -483,6 +505,7 @@ __global__ void __launch_bounds__(256, SHARD ? 3 : 4)
         if (f < F) {
           if (hints) stg_stream_f4_pol(xrow + (int64_t)f * dim + chunk * 4, v[u], pol_stream);
           else stg_stream_f4(xrow + (int64_t)f * dim + chunk * 4, v[u]);
+          if (PLANES) store_planes4(p, b * p.xp_pitch + (int64_t)f * dim + chunk * 4, v[u]);
           if ((p.fm_mask >> f) & 1ull) {
             s.x += v[u].x; s.y += v[u].y; s.z += v[u].z; s.w += v[u].w;
             q += v[u].x * v[u].x + v[u].y * v[u].y + v[u].z * v[u].z + v[u].w * v[u].w;
@@ -523,6 +546,15 @@ __global__ void __launch_bounds__(256, SHARD ? 3 : 4)
     for (int64_t c = c0 + lane; c < p.x_cols; c += 32) {
       const int j = (int)(c - c0);
       xrow[c] = j < p.ndense ? p.dense[b * p.dense_ld + j] : 0.f;
+    }
+    if (PLANES) {
+      for (int64_t c = c0 + lane; c < p.xp_pitch; c += 32) {
+        const int j = (int)(c - c0);
+        const float v = j < p.ndense ? p.dense[b * p.dense_ld + j] : 0.f;
+        const __nv_bfloat16 h = __float2bfloat16_rn(v);
+        p.xp_hi[b * p.xp_pitch + c] = h;
+        p.xp_lo[b * p.xp_pitch + c] = __float2bfloat16_rn(v - __bfloat162float(h));
+      }
     }
     id0 = nid0;
     id1 = nid1;
@@ -759,6 +791,8 @@ static b2ctr_status_t fill_uni(const b2ctr_uniform_gather_t* g, UniParams* p) {
     p->lin[f] = (g->lin_tables && g->world <= 1) ? g->lin_tables[f] : nullptr;
     B2_REQUIRE(g->world > 1 || !g->lin_tables || p->lin[f], "uniform gather: lin_tables[%d] is NULL", f);
   }
+  p->xp_hi = p->xp_lo = nullptr;
+  p->xp_pitch = 0;
   p->world = g->world > 1 ? g->world : 1;
   p->wshift = 0;
   p->peer_tab = g->peer_tables;
@@ -851,9 +885,40 @@ b2ctr_status_t b2ctr_embed_gather_uniform_fwd(const b2ctr_uniform_gather_t* g, i
   b2ctr_status_t s = fill_uni(g, &p);
   if (s != B2CTR_OK) return s;
   if (batch <= 0) return B2CTR_OK;
+  if (g->x_planes) {
+    B2_REQUIRE(batch % 256 == 0, "uniform gather: x_planes needs a batch that is a multiple of 256 (got %lld)",
+               (long long)batch);
+    B2_REQUIRE(g->x_planes_cols >= (int64_t)g->nfeat * p.dim + g->ndense && g->x_planes_cols <= p.x_cols,
+               "uniform gather: x_planes_cols out of range");
+    B2_REQUIRE(aligned16(g->x_planes), "uniform gather: x_planes must be 16-byte aligned");
+    p.xp_pitch = planes_cols_pad(g->x_planes_cols);
+    p.xp_hi = (__nv_bfloat16*)g->x_planes;
+    p.xp_lo = p.xp_hi + planes_rows_pad(batch) * p.xp_pitch;
+  }
   cudaStream_t st = (cudaStream_t)stream;
   const int grid = grid_for(batch, 8, 8);
-  B2_DISPATCH_LPR(gather_uniform_fwd_kernel, p.dim, p, batch);
+#define B2_GATHER_CASE(LPRV)                                                                         \
+  case LPRV:                                                                                         \
+    if (p.world > 1) {                                                                               \
+      if (p.xp_hi) gather_uniform_fwd_kernel<LPRV, true, true><<<grid, 256, 0, st>>>(p, batch);      \
+      else gather_uniform_fwd_kernel<LPRV, true, false><<<grid, 256, 0, st>>>(p, batch);             \
+    } else {                                                                                         \
+      if (p.xp_hi) gather_uniform_fwd_kernel<LPRV, false, true><<<grid, 256, 0, st>>>(p, batch);     \
+      else gather_uniform_fwd_kernel<LPRV, false, false><<<grid, 256, 0, st>>>(p, batch);            \
+    }                                                                                                \
+    break;
+  switch (p.dim / 4) {
+    B2_GATHER_CASE(1) B2_GATHER_CASE(2) B2_GATHER_CASE(4) B2_GATHER_CASE(8) B2_GATHER_CASE(16)
+    default:
+      if (p.world > 1) {
+        if (p.xp_hi) gather_uniform_fwd_kernel<32, true, true><<<grid, 256, 0, st>>>(p, batch);
+        else gather_uniform_fwd_kernel<32, true, false><<<grid, 256, 0, st>>>(p, batch);
+      } else {
+        if (p.xp_hi) gather_uniform_fwd_kernel<32, false, true><<<grid, 256, 0, st>>>(p, batch);
+        else gather_uniform_fwd_kernel<32, false, false><<<grid, 256, 0, st>>>(p, batch);
+      }
+  }
+#undef B2_GATHER_CASE
   B2_CHECK_LAUNCH("b2ctr_embed_gather_uniform_fwd");
   return B2CTR_OK;
 }

@@ -1064,7 +1064,6 @@ static inline int64_t round_up(int64_t v, int64_t q) { return (v + q - 1) / q * 
 // (M tile of an MN-major A, N tiles of an MN-major B); narrow matrices (<= 64 columns) pad to one 64-wide
 // swizzle atom only - a 128-wide MN-major tile then runs into the next plane row, which only feeds output
 // rows/columns >= m/n that are never stored.
-static inline int64_t planes_cols_pad(int64_t cols) { return cols <= 64 ? 64 : round_up(cols, 128); }
 static inline int planes_bn(int64_t n, int64_t k) {
   if (n <= 32) return 32;
   if (n <= 64) return 64;

@@ -550,6 +550,15 @@ class EmbeddingPlanner(object):
             plan.g.x_cols = self.main_ld if only_fast else self.fast_n * fast_slots[0].dim
             if peer is not None:
                 plan.set_peers(self.dist.world, peer[0].table, peer[1].table if peer[1] is not None else None)
+            from . import ops as _ops
+            if (only_fast and self.tail_done is not None and batch % 256 == 0 and batch >= 256
+                    and _ops.GEMM_PRECISION == L.GEMM_BF16X3 and _ops.PLANE_REUSE and _ops.GATHER_PLANES):
+                # the DNN reads x[:, :F*E+nd] as its first GEMM operand: emit its bf16 hi/lo planes here
+                kd = self.main_width + self.tail_done[1]
+                xp = torch.empty((L.lib().b2ctr_planes_bytes(batch, kd),), dtype=torch.uint8, device=dev)
+                plan.g.x_planes = xp.data_ptr()
+                plan.g.x_planes_cols = kd
+                bufs["main"].xplanes = (kd, xp)
             K.embed_gather_uniform_fwd(plan, batch)
             if fm is not None:
                 self.fm_result = (self.fm_hint, E.Var(fm.reshape(batch, 1)))

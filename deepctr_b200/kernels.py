@@ -128,7 +128,24 @@ class UniformPlan(object):
         self.g.peer_lin_tables = peer_lin_tables.data_ptr() if peer_lin_tables is not None else None
 
 
+_l2_granule_done = set()
+
+
+def _l2_fetch_hint():
+    """Once per device: DRAM -> L2 fetch granule for the random-row embedding traffic (B2CTR_L2_FETCH=32|64|128,
+    0 = leave the driver default)."""
+    dev = torch.cuda.current_device()
+    if dev in _l2_granule_done:
+        return
+    _l2_granule_done.add(dev)
+    import os
+    want = int(os.environ.get("B2CTR_L2_FETCH", "0"))
+    if want:
+        L.check(L.lib().b2ctr_set_l2_fetch_granularity(want), "set_l2_fetch_granularity")
+
+
 def embed_gather_uniform_fwd(plan, batch):
+    _l2_fetch_hint()
     L.check(L.lib().b2ctr_embed_gather_uniform_fwd(C.byref(plan.g), batch, stream()),
             "embed_gather_uniform_fwd")
 

@@ -17,6 +17,8 @@ GEMM_PRECISION = L.GEMM_BF16X3
 # BF16X3: split every GEMM operand into bf16 planes once per step and reuse them (needs MN-major operands,
 # i.e. tc variant 3)
 PLANE_REUSE = True
+# the fused embedding gather also writes the planes of the first DNN operand (saves re-reading X to split it)
+GATHER_PLANES = True
 
 
 # bumped by ops whose kernels take per-step by-value state (dropout seeds) or that need the host (string
@@ -60,6 +62,11 @@ def _as2d(x):
 def _planes_of(var, t2):
     """bf16 hi/lo planes of a Var's 2-D view, split once per step and shared by every GEMM that reads it
     (forward of each consumer + the wgrad GEMMs)."""
+    base = var.base
+    if (base is not None and base.xplanes is not None and var.col0 == 0 and base.data is not None
+            and base.xplanes[0] == t2.shape[1] and t2.data_ptr() == base.data.data_ptr()
+            and t2.stride(0) == base.data.stride(0)):
+        return base.xplanes[1]       # the fused gather already wrote the planes of this window
     key = (t2.data_ptr(), tuple(t2.shape), t2.stride(0))
     if var.planes is None or var.planes[0] != key:
         var.planes = (key, K.split_planes(t2))

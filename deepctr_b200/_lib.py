@@ -86,6 +86,7 @@ SIGNATURES = {
     "b2ctr_split_planes": (_i32, [_vp, _i64, _i64, _i64, _vp, _vp]),
     "b2ctr_bias_act_bwd_workspace_bytes": (_sz, [_i64, _i64]),
     "b2ctr_bias_act_bwd": (_i32, [_vp, _vp, _vp, _vp, _i64, _i64, _i64, _i32, _vp, _sz, _vp]),
+    "b2ctr_bias_act_bwd_planes": (_i32, [_vp, _vp, _vp, _vp, _vp, _i64, _i64, _i64, _i32, _vp, _sz, _vp]),
     "b2ctr_act_fwd": (_i32, [_vp, _vp, _i64, _i32, _vp]),
     "b2ctr_add_n": (_i32, [C.POINTER(_vp), C.POINTER(_f32), _i32, _vp, _i64, _vp]),
     "b2ctr_axpy": (_i32, [_vp, _vp, _f32, _i64, _vp]),

@@ -1,6 +1,7 @@
 // elementwise.cu — activation backward + bias gradient, n-ary add, strided copies, FM operator,
 // prediction head + loss, optimizers.  All HBM-bound: 128-bit accesses where alignment allows,
 // grid-stride loops on grids that are whole multiples of the SM count.
+#include <cuda_bf16.h>
 #include "common.cuh"
 
 namespace b2ctr {
@@ -48,7 +49,8 @@ __global__ void __launch_bounds__(256)
 // row groups are combined through shared memory in a fixed order.
 __global__ void __launch_bounds__(256)
     bias_act_bwd_vec4_kernel(const float* __restrict__ dy, const float* __restrict__ y, float* dz,
-                             float* partial, int64_t m, int64_t n, int64_t ld, int act) {
+                             float* partial, int64_t m, int64_t n, int64_t ld, int act,
+                             __nv_bfloat16* pl_hi, __nv_bfloat16* pl_lo, int64_t pl_pitch) {
   __shared__ float4 red[256];
   const int cgs = (int)(n >> 2);              // column groups
   const int rgs = 256 / cgs;                  // row groups per pass
@@ -66,6 +68,20 @@ __global__ void __launch_bounds__(256)
       g.z *= act_grad_from_out(yy.z, act); g.w *= act_grad_from_out(yy.w, act);
     }
     if (dz) *reinterpret_cast<float4*>(dz + o) = g;
+    if (pl_hi) {     // bf16 hi/lo operand planes of dz for the dgrad / wgrad GEMMs (b2ctr_split_planes layout)
+      const __nv_bfloat16 h0 = __float2bfloat16_rn(g.x), h1 = __float2bfloat16_rn(g.y);
+      const __nv_bfloat16 h2 = __float2bfloat16_rn(g.z), h3 = __float2bfloat16_rn(g.w);
+      uint2 h, l;
+      h.x = (uint32_t)__bfloat16_as_ushort(h0) | ((uint32_t)__bfloat16_as_ushort(h1) << 16);
+      h.y = (uint32_t)__bfloat16_as_ushort(h2) | ((uint32_t)__bfloat16_as_ushort(h3) << 16);
+      l.x = (uint32_t)__bfloat16_as_ushort(__float2bfloat16_rn(g.x - __bfloat162float(h0))) |
+            ((uint32_t)__bfloat16_as_ushort(__float2bfloat16_rn(g.y - __bfloat162float(h1))) << 16);
+      l.y = (uint32_t)__bfloat16_as_ushort(__float2bfloat16_rn(g.z - __bfloat162float(h2))) |
+            ((uint32_t)__bfloat16_as_ushort(__float2bfloat16_rn(g.w - __bfloat162float(h3))) << 16);
+      const int64_t po = r * pl_pitch + cg * 4;
+      *reinterpret_cast<uint2*>(pl_hi + po) = h;
+      *reinterpret_cast<uint2*>(pl_lo + po) = l;
+    }
     s.x += g.x; s.y += g.y; s.z += g.z; s.w += g.w;
   }
   if (partial) {
@@ -339,7 +355,13 @@ size_t b2ctr_bias_act_bwd_workspace_bytes(int64_t m, int64_t n) {
 b2ctr_status_t b2ctr_bias_act_bwd(const float* dy, const float* y, float* dz, float* dbias, int64_t m,
                                   int64_t n, int64_t ld, int32_t act, void* workspace,
                                   size_t workspace_bytes, void* stream) {
-  B2_REQUIRE(dy && (dz || dbias), "bias_act_bwd: NULL dy, or nothing to compute");
+  return b2ctr_bias_act_bwd_planes(dy, y, dz, dbias, nullptr, m, n, ld, act, workspace, workspace_bytes, stream);
+}
+
+b2ctr_status_t b2ctr_bias_act_bwd_planes(const float* dy, const float* y, float* dz, float* dbias, void* dz_planes,
+                                         int64_t m, int64_t n, int64_t ld, int32_t act, void* workspace,
+                                         size_t workspace_bytes, void* stream) {
+  B2_REQUIRE(dy && (dz || dbias || dz_planes), "bias_act_bwd: NULL dy, or nothing to compute");
   B2_REQUIRE(act == B2CTR_ACT_NONE || y, "bias_act_bwd: activation output y required");
   B2_REQUIRE(ld >= n, "bias_act_bwd: ld < n");
   if (m <= 0 || n <= 0) return B2CTR_OK;
@@ -354,9 +376,18 @@ b2ctr_status_t b2ctr_bias_act_bwd(const float* dy, const float* y, float* dz, fl
   const bool vec = n % 4 == 0 && n / 4 <= 256 && 256 % (n / 4) == 0 && ld % 4 == 0 &&
                    ((uintptr_t)dy & 15) == 0 && (!y || ((uintptr_t)y & 15) == 0) &&
                    (!dz || ((uintptr_t)dz & 15) == 0);
+  __nv_bfloat16 *pl_hi = nullptr, *pl_lo = nullptr;
+  const int64_t pl_pitch = planes_cols_pad(n);
+  if (dz_planes) {
+    // the planes are written row by row for [0, m) x [0, n): no padding may exist
+    B2_REQUIRE(vec && m % 256 == 0 && pl_pitch == n && ((uintptr_t)dz_planes & 15) == 0,
+               "bias_act_bwd: dz_planes needs m %% 256 == 0, n in {64, 128k} and the vectorised layout");
+    pl_hi = (__nv_bfloat16*)dz_planes;
+    pl_lo = pl_hi + planes_rows_pad(m) * pl_pitch;
+  }
   if (vec)
     bias_act_bwd_vec4_kernel<<<(unsigned)nblocks, 256, 0, ST>>>(dy, y, dz, dbias ? (float*)workspace : nullptr,
-                                                               m, n, ld, act);
+                                                               m, n, ld, act, pl_hi, pl_lo, pl_pitch);
   else
     bias_act_bwd_kernel<<<(unsigned)nblocks, 256, 0, ST>>>(dy, y, dz, dbias ? (float*)workspace : nullptr,
                                                           m, n, ld, act);

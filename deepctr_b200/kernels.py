@@ -212,7 +212,14 @@ def split_planes(x2d):
 
 
 # ---- elementwise ----------------------------------------------------------------------------
-def bias_act_bwd(dy, y, act, want_dz=True, want_dbias=True, m=None, n=None):
+def planes_fusable(m, n):
+    """bias_act_bwd can write the operand planes of dz itself (no padding inside the planes, vector layout)."""
+    return m % 256 == 0 and (n == 64 or n % 128 == 0) and n % 4 == 0 and n // 4 <= 256 and 256 % (n // 4) == 0
+
+
+def bias_act_bwd(dy, y, act, want_dz=True, want_dbias=True, m=None, n=None, want_planes=False):
+    """dz = dy * act'(y), dbias = colsum(dz); with want_planes also the bf16 operand planes of dz
+    (returned as third value)."""
     _require_cuda(dy, y)
     if m is None:
         m, n = dy.shape[0], dy.shape[1]
@@ -221,6 +228,11 @@ def bias_act_bwd(dy, y, act, want_dz=True, want_dbias=True, m=None, n=None):
     dbias = torch.empty((n,), dtype=torch.float32, device=dy.device) if want_dbias else None
     nbytes = L.lib().b2ctr_bias_act_bwd_workspace_bytes(m, n) if want_dbias else 0
     ws = workspace(nbytes, dy.device)
+    if want_planes:
+        planes = torch.empty((L.lib().b2ctr_planes_bytes(m, n),), dtype=torch.uint8, device=dy.device)
+        L.check(L.lib().b2ctr_bias_act_bwd_planes(ptr(dy), ptr(y), ptr(dz), ptr(dbias), ptr(planes), m, n, ld, act,
+                                                  ptr(ws), nbytes, stream()), "bias_act_bwd_planes")
+        return dz, dbias, planes
     L.check(L.lib().b2ctr_bias_act_bwd(ptr(dy), ptr(y), ptr(dz), ptr(dbias), m, n, ld, act, ptr(ws),
                                        nbytes, stream()), "bias_act_bwd")
     return dz, dbias

@@ -18,7 +18,7 @@ GEMM_PRECISION = L.GEMM_BF16X3
 # i.e. tc variant 3)
 PLANE_REUSE = True
 # the fused embedding gather also writes the planes of the first DNN operand (saves re-reading X to split it)
-GATHER_PLANES = True
+GATHER_PLANES = False    # measured: -11 us/step but +60 us inside the gather kernel itself; opt-in
 
 
 # bumped by ops whose kernels take per-step by-value state (dropout seeds) or that need the host (string
@@ -98,13 +98,19 @@ def dense(x, w, b=None, activation=None):
         if not dy.is_contiguous():
             dy = dy.contiguous()
         need_db = b is not None and b.requires_grad
+        need_planes = reuse and (x.requires_grad or w.requires_grad)
+        dzp = None
         if fused_act != L.ACT_NONE or need_db:
-            dz, db = K.bias_act_bwd(dy, y, fused_act, want_dz=fused_act != L.ACT_NONE, want_dbias=need_db)
+            if need_planes and fused_act != L.ACT_NONE and dy.stride(0) % 4 == 0 and K.planes_fusable(m, n):
+                dz, db, dzp = K.bias_act_bwd(dy, y, fused_act, want_dz=True, want_dbias=need_db, want_planes=True)
+            else:
+                dz, db = K.bias_act_bwd(dy, y, fused_act, want_dz=fused_act != L.ACT_NONE, want_dbias=need_db)
             if dz is None:
                 dz = dy
         else:
             dz, db = dy, None
-        dzp = K.split_planes(dz) if reuse and (x.requires_grad or w.requires_grad) else None
+        if need_planes and dzp is None:
+            dzp = K.split_planes(dz)
         if x.requires_grad:
             base = x.base
             if (base is not None and x.col0 == 0 and x.ncols != -1 and base.data.dim() == 2

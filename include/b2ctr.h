@@ -234,6 +234,13 @@ B2CTR_API b2ctr_status_t b2ctr_bias_act_bwd(const float* dy, const float* y, flo
                                            float* dbias, int64_t m, int64_t n, int64_t ld,
                                            int32_t act, void* workspace, size_t workspace_bytes,
                                            void* stream);
+/* Same, and additionally the bf16 hi/lo operand planes of dz (b2ctr_split_planes layout) for the dgrad /
+ * wgrad GEMMs that consume dz next - saves the separate split pass.  Requires m % 256 == 0 and
+ * n == 64 or n % 128 == 0 (no padding inside the planes), n / 4 dividing 256. */
+B2CTR_API b2ctr_status_t b2ctr_bias_act_bwd_planes(const float* dy, const float* y, float* dz, float* dbias,
+                                                  void* dz_planes, int64_t m, int64_t n, int64_t ld,
+                                                  int32_t act, void* workspace, size_t workspace_bytes,
+                                                  void* stream);
 /* y = act(x) elementwise over n contiguous elements */
 B2CTR_API b2ctr_status_t b2ctr_act_fwd(const float* x, float* y, int64_t n, int32_t act,
                                       void* stream);

@@ -308,3 +308,19 @@ def test_gemm_bf16x3_splitk_accumulate(cuda, variant):
     c2 = c0.to(cuda)
     K.gemm(xd, dy, c=c2, trans_a=True, accumulate=True, split_k=8, alpha=0.5, m=m, n=n, k=k)
     torch.testing.assert_close(c.cpu(), c2.cpu(), rtol=1e-4, atol=2e-3)
+
+
+@pytest.mark.parametrize("m,n", [(512, 256), (256, 128), (1024, 64)])
+def test_bias_act_bwd_emits_operand_planes(cuda, m, n):
+    """b2ctr_bias_act_bwd_planes: dz, dbias unchanged, planes identical to b2ctr_split_planes(dz)."""
+    K, L = _kern()
+    rng = np.random.RandomState(m + n)
+    dy, y = _r(rng, m, n).to(cuda), torch.relu(_r(rng, m, n)).to(cuda)
+    dz0, db0 = K.bias_act_bwd(dy, y, L.ACT_RELU)
+    assert K.planes_fusable(m, n) and not K.planes_fusable(m + 1, n) and not K.planes_fusable(m, 96)
+    dz, db, planes = K.bias_act_bwd(dy, y, L.ACT_RELU, want_planes=True)
+    assert torch.equal(dz, dz0) and torch.equal(db, db0)
+    want = K.split_planes(dz0)
+    assert torch.equal(planes[:-256], want[:-256])
+    with pytest.raises(ValueError):
+        K.bias_act_bwd(dy[:m - 1], y[:m - 1], L.ACT_RELU, want_planes=True)

@@ -398,6 +398,14 @@ def main():
                 "algorithmic_bytes_per_launch": bytes_per_sample * B}
     roof_gather = frac_hbm("embed_gather_uniform_fwd", gather_fwd_bytes)
     roof_scatter = frac_hbm("embed_scatter_uniform_bwd", scatter_bwd_bytes)
+    # DRAM bytes per launch from the committed ncu --set full captures of this workload (profiles/README.md)
+    traffic = {}
+    tpath = os.path.join(ROOT, "profiles", "r1_traffic.json")
+    if os.path.exists(tpath) and args.config == "c2" and world == 1:
+        traffic = json.load(open(tpath))
+    for r in (roof_gather, roof_scatter):
+        if r is not None and r["kernel"] in traffic:
+            r["traffic"] = traffic[r["kernel"]]
     gemm_ms = sum(v[1] for k, v in prof.items() if k.startswith("gemm"))
     # the DNN GEMM launches, each timed alone on the device (the eager per-group events above include the host's
     # launch gaps): algorithmic flops = 2*M*N*K per launch; in bf16x3 mode the tensor pipe executes 3x that

@@ -184,3 +184,18 @@ def test_host_pack_native_thread_pool():
             assert (dst[o + len(b):o + len(b) + gap] == 255).all()      # nothing written between blocks
     with pytest.raises(ValueError):
         L.check(L.lib().b2ctr_host_pack(None, None, None, 2, None, 0), "host_pack")
+
+
+def test_dense_gemm_policy_helpers():
+    """Pure host logic of ops.dense: split-K sizing for CTA-pair tiles and the conditions under which the
+    producer of dZ can write its operand planes itself."""
+    from deepctr_b200 import ops, kernels as K
+    assert ops._split_k(845, 256, 65536) == 18            # 4 pair tiles x 18 K slices = 72 of 74 SM pairs
+    assert ops._split_k(256, 128, 65536) == 64            # one tile: capped by K / 1024
+    assert ops._split_k(64, 1, 65536) == 64
+    assert ops._split_k(845, 256, 2048) == 1              # short reductions are not split
+    assert ops._split_k(30000, 30000, 1 << 20) == 1       # more tiles than SM pairs
+    assert K.planes_fusable(65536, 256) and K.planes_fusable(65536, 128) and K.planes_fusable(65536, 64)
+    assert not K.planes_fusable(65536, 1) and not K.planes_fusable(65537, 256) and not K.planes_fusable(256, 96)
+    assert not K.planes_fusable(256, 2048)                # wider than one vectorised row group
+    assert ops.GEMM_PRECISION == __import__("deepctr_b200._lib", fromlist=["x"]).GEMM_BF16X3

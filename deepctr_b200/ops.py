@@ -384,38 +384,33 @@ def fm(x):
 
 
 def add_bias(x, b):
-    """x + b for a scalar / per-column bias (Linear use_bias, layers/utils.py:172-173)."""
-    zeros = zeros_like_batch(x, 1)
-    ones = E.Var(K.fill(torch.empty((1, 1), dtype=torch.float32, device=x.data.device), 1.0))
-    # [B,1] = x + 1 * b  via the GEMM epilogue: dense([B,1] of ones) would cost the same; use add_n on a
-    # broadcast built by the gemm kernel (outer product ones[B,1] x b[1,1])
+    """x + b over the last axis for a per-column (or scalar, when the last axis is 1) bias:
+    Linear(use_bias=True) without a dense part, layers/utils.py:172-173.  Forward = copy + rank-1 update
+    ones[B,1] @ b[1,n] through the skinny GEMM kernel; backward = pass-through and a column sum."""
+    xt = E.contiguous(x)
+    x2 = xt.reshape(-1, xt.shape[-1])
+    m, n = x2.shape
     bd = b.materialize() if isinstance(b, E.Weight) else b.data
-    col = torch.empty((x.data.shape[0], 1), dtype=torch.float32, device=x.data.device)
-    K.fill(col, 1.0)
-    colv = E.Var(col)
-    bvar = b
-    return add_n([x, dense(colv, _as_kernel(bvar), None, None)])
+    if bd.numel() != n:
+        raise ValueError("add_bias: bias has %d elements, last axis has %d" % (bd.numel(), n))
+    y = K.add_n([x2])                                     # copy
+    ones = K.fill(torch.empty((m, 1), dtype=torch.float32, device=y.device), 1.0)
+    K.gemm(ones, bd.reshape(1, n), c=y, accumulate=True, m=m, n=n, k=1)
+    out = E.Var(y.reshape(x.data.shape))
 
+    def bwd(grads):
+        dy = grads[0]
+        if x.requires_grad:
+            E.add_grad(x, dy)
+        if b.requires_grad:
+            dy2 = dy.reshape(m, n)
+            if not dy2.is_contiguous():
+                dy2 = dy2.contiguous()
+            _, db = K.bias_act_bwd(dy2, None, L.ACT_NONE, want_dz=False, want_dbias=True)
+            E.add_grad(b, db.reshape(bd.shape))
 
-def _as_kernel(b):
-    """view a [n] bias weight as a [1, n] kernel sharing storage and gradient."""
-    data = b.materialize() if isinstance(b, E.Weight) else b.data
-    v = E.Var(data.reshape(1, -1), requires_grad=b.requires_grad)
-    v.base, v.col0, v.ncols = b, 0, -1
-    v.shape_ = (1, data.numel())
-    return _KernelView(v, b)
-
-
-class _KernelView(E.Var):
-    __slots__ = ("shape_",)
-
-    def __init__(self, v, b):
-        E.Var.__init__(self, v.data, requires_grad=b.requires_grad, base=b, col0=0, ncols=-1)
-        self.shape_ = tuple(v.data.shape)
-
-    @property
-    def shape(self):
-        return self.shape_
+    E.record([out], [x, b], bwd)
+    return out
 
 
 # ==================================================================================================

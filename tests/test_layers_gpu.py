@@ -299,6 +299,14 @@ def test_prediction_and_linear_layers(cuda):
     want = O.linear(torch.from_numpy(sp), torch.from_numpy(dn), torch.from_numpy(lin.kernel.value()),
                     torch.tensor([0.5]))
     _close(got, want.numpy())
+    # mode 0 (sparse part only) with a bias: rowsum + scalar bias, gradients to the input and to the bias
+    lin0 = Linear(mode=0, use_bias=True)
+    lin0.build((None, 1, 6))
+    lin0.bias.set_value(np.array([-0.75], np.float32))
+    out, gy, gin, gw = _run(lin0, sp, rng, training=True)
+    _close(out, sp.sum(-1) - 0.75)
+    _close(gin[0], np.broadcast_to(gy.reshape(20, 1, 1), sp.shape))
+    _close([v for n, v in gw.items() if n.endswith("linear_bias")][0], gy.sum().reshape(1), 1e-4, 1e-5)
 
 
 def test_hash_layer_device_and_vocabulary(cuda, tmp_path):

@@ -246,12 +246,13 @@ def main():
         sb = min(args.cpu_sample_batch, cfg["batch"])
         v, ms, threads = run_cpu(cfg, max(1, min(args.steps, 10)), min(warmup, 3), sb)
         line = {"impl": "reference", "metric": "samples/sec fwd+bwd DeepFM Criteo-synth", "value": v,
-                "unit": "samples/s", "n_gpus": 0, "steps": min(args.steps, 10), "warmup": min(warmup, 3),
+                "unit": "samples/s", "n_gpus": args.gpus, "steps": min(args.steps, 10), "warmup": min(warmup, 3),
                 "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
                 "dtype": "f32", "data": "synthetic",
                 "config": {"workload": cfg["workload"], "global_batch": sb, "optimizer": "sgd",
-                           "note": "oracle port (torch-CPU restatement of the reference math); TensorFlow is "
-                                   "not installable here; each step is a %d-sample slice of the batch" % sb},
+                           "note": "CPU arm (no GPU is used; n_gpus echoes the launch): oracle port = torch-CPU "
+                                   "restatement of the reference math; TensorFlow is not installable here; each "
+                                   "step is a %d-sample slice of the batch" % sb},
                 "cpu_baseline": {"value": v, "unit": "samples/s", "cores": threads, "kind": "port",
                                  "sample": "%d steps x %d samples of the c2 workload" % (min(args.steps, 10), sb)},
                 "e2e": {"value": v, "unit": "samples/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}

@@ -101,6 +101,9 @@ SIGNATURES = {
     "b2ctr_predict_loss": (_i32, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _i64, _i32, _vp]),
     "b2ctr_sgd_step": (_i32, [_vp, _vp, _f32, _f32, _i64, _vp]),
     "b2ctr_adam_step": (_i32, [_vp, _vp, _vp, _vp, _f32, _f32, _f32, _f32, _f32, _i64, _i64, _vp]),
+    "b2ctr_adam_step_dev": (_i32, [_vp, _vp, _vp, _vp, C.c_float, C.c_float, C.c_float, C.c_float, C.c_float, _vp,
+                            _i64, _vp]),
+    "b2ctr_counter_add": (_i32, [_vp, _i64, _vp]),
     "b2ctr_adagrad_step": (_i32, [_vp, _vp, _vp, _f32, _f32, _f32, _i64, _vp]),
     "b2ctr_ewise": (_i32, [_i32, _vp, _vp, _vp, _vp, _i64, _i32, _vp]),
     "b2ctr_cross_vector_fwd": (_i32, [_vp, _i64, _vp, _i64, _vp, _vp, _vp, _vp, _i64, _i32, _vp]),

@@ -558,6 +558,41 @@ b2ctr_status_t b2ctr_adam_step(float* w, const float* g, float* m, float* v, flo
   return B2CTR_OK;
 }
 
+// Adam with the step count in device memory: nothing step-dependent is passed by value, so the launch can be
+// part of a replayed CUDA graph (the counter is advanced once per step by b2ctr_counter_add).
+__global__ void adam_dev_kernel(float* w, const float* __restrict__ g, float* m, float* v, float lr, float b1,
+                                float b2, float eps, float l2, const int64_t* __restrict__ step, int64_t n) {
+  const double t = (double)(*step);
+  const float lr_t = (float)((double)lr * sqrt(1.0 - pow((double)b2, t)) / (1.0 - pow((double)b1, t)));
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n;
+       i += (int64_t)gridDim.x * blockDim.x) {
+    const float gi = g[i] + 2.f * l2 * w[i];
+    const float mi = b1 * m[i] + (1.f - b1) * gi;
+    const float vi = b2 * v[i] + (1.f - b2) * gi * gi;
+    m[i] = mi;
+    v[i] = vi;
+    w[i] -= lr_t * mi / (sqrtf(vi) + eps);
+  }
+}
+__global__ void counter_add_kernel(int64_t* c, int64_t delta) { *c += delta; }
+
+b2ctr_status_t b2ctr_adam_step_dev(float* w, const float* g, float* m, float* v, float lr, float beta1,
+                                   float beta2, float eps, float l2, const int64_t* step_dev, int64_t n,
+                                   void* stream) {
+  B2_REQUIRE(w && g && m && v && step_dev, "adam_step_dev: NULL pointer");
+  if (n <= 0) return B2CTR_OK;
+  adam_dev_kernel<<<grid_for(n, 256, 8), 256, 0, ST>>>(w, g, m, v, lr, beta1, beta2, eps, l2, step_dev, n);
+  B2_CHECK_LAUNCH("b2ctr_adam_step_dev");
+  return B2CTR_OK;
+}
+
+b2ctr_status_t b2ctr_counter_add(int64_t* counter, int64_t delta, void* stream) {
+  B2_REQUIRE(counter, "counter_add: NULL pointer");
+  counter_add_kernel<<<1, 1, 0, ST>>>(counter, delta);
+  B2_CHECK_LAUNCH("b2ctr_counter_add");
+  return B2CTR_OK;
+}
+
 b2ctr_status_t b2ctr_adagrad_step(float* w, const float* g, float* acc, float lr, float eps, float l2,
                                   int64_t n, void* stream) {
   B2_REQUIRE(w && g && acc, "adagrad_step: NULL pointer");

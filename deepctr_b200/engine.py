@@ -756,6 +756,16 @@ class Lambda(Layer):
 class Optimizer(object):
     def __init__(self, name, lr):
         self.name, self.lr, self.iterations = name, lr, 0
+        self.step_dev = None        # Adam: step count in device memory (advanced once per step, see begin_step)
+
+    def begin_step(self):
+        """Called once per training step before the first apply().  Adam keeps its step count on the device so
+        that the whole step, optimizer included, is replayable as a CUDA graph."""
+        if self.name == "adam":
+            if self.step_dev is None:
+                self.step_dev = torch.empty((1,), dtype=torch.int64, device=device())
+                self.step_dev.copy_(torch.tensor([self.iterations - 1], dtype=torch.int64))
+            K.counter_add(self.step_dev, 1)
 
     def apply(self, w):
         g = w.grad
@@ -772,7 +782,10 @@ class Optimizer(object):
                 st["v"] = torch.zeros_like(w.data)
                 K.fill(st["m"], 0.0)
                 K.fill(st["v"], 0.0)
-            K.adam_step(w.data, g, st["m"], st["v"], self.lr, self.iterations, l2=w.l2)
+            if self.step_dev is not None:
+                K.adam_step_dev(w.data, g, st["m"], st["v"], self.lr, self.step_dev, l2=w.l2)
+            else:
+                K.adam_step(w.data, g, st["m"], st["v"], self.lr, self.iterations, l2=w.l2)
         elif self.name == "adagrad":
             st = w.opt_state
             if "acc" not in st:
@@ -1073,8 +1086,6 @@ class Model(object):
         if getattr(self, "dist", None) is not None and getattr(self.planner, "sharded", False) \
                 and not getattr(self.planner, "peer_mode", False):
             return False                       # NCCL all-to-all transport: split sizes are read on the host
-        if self.optimizer.name == "adam":      # step-dependent bias correction is a by-value kernel argument
-            return False
         return ops.UNCAPTURABLE == self._uncapturable0
 
     def _graph_key(self, feed, labels):
@@ -1145,6 +1156,7 @@ class Model(object):
                     lambda src, flat, off: K.copy2d(src.reshape(1, -1), src.numel(), flat, flat.numel(), 1,
                                                     src.numel(), dst_off=off),
                     lambda flat, f: K.add_n([flat], scales=[f], out=flat))
+            self.optimizer.begin_step()
             for w in dense:
                 self.optimizer.apply(w)
         return loss_sum, pred, lt.shape[0]

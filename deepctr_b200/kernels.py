@@ -363,6 +363,18 @@ def adam_step(w, g, m, v, lr, step, beta1=0.9, beta2=0.999, eps=1e-7, l2=0.0):
                                     w.numel(), stream()), "adam_step")
 
 
+def adam_step_dev(w, g, m, v, lr, step_dev, beta1=0.9, beta2=0.999, eps=1e-7, l2=0.0):
+    """Adam with the step count read from the device tensor `step_dev` (int64 [1]): graph-replayable."""
+    _require_cuda(w, g, m, v, step_dev)
+    L.check(L.lib().b2ctr_adam_step_dev(ptr(w), ptr(g), ptr(m), ptr(v), lr, beta1, beta2, eps, l2, ptr(step_dev),
+                                        w.numel(), stream()), "adam_step_dev")
+
+
+def counter_add(counter, delta=1):
+    _require_cuda(counter)
+    L.check(L.lib().b2ctr_counter_add(ptr(counter), delta, stream()), "counter_add")
+
+
 def adagrad_step(w, g, acc, lr, eps=1e-7, l2=0.0):
     _require_cuda(w, g, acc)
     L.check(L.lib().b2ctr_adagrad_step(ptr(w), ptr(g), ptr(acc), lr, eps, l2, w.numel(), stream()),

@@ -295,6 +295,13 @@ B2CTR_API b2ctr_status_t b2ctr_sgd_step(float* w, const float* g, float lr, floa
 B2CTR_API b2ctr_status_t b2ctr_adam_step(float* w, const float* g, float* m, float* v, float lr,
                                         float beta1, float beta2, float eps, float l2,
                                         int64_t step, int64_t n, void* stream);
+/* Same update with the step count t read from device memory (>= 1 when the kernel runs): no step-dependent
+ * by-value argument, so the launch can live in a replayed CUDA graph.  b2ctr_counter_add advances the counter
+ * (once per training step, before the first b2ctr_adam_step_dev of the step). */
+B2CTR_API b2ctr_status_t b2ctr_adam_step_dev(float* w, const float* g, float* m, float* v, float lr,
+                                            float beta1, float beta2, float eps, float l2,
+                                            const int64_t* step_dev, int64_t n, void* stream);
+B2CTR_API b2ctr_status_t b2ctr_counter_add(int64_t* counter, int64_t delta, void* stream);
 B2CTR_API b2ctr_status_t b2ctr_adagrad_step(float* w, const float* g, float* acc, float lr,
                                            float eps, float l2, int64_t n, void* stream);
 

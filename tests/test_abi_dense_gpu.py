@@ -324,3 +324,23 @@ def test_bias_act_bwd_emits_operand_planes(cuda, m, n):
     assert torch.equal(planes[:-256], want[:-256])
     with pytest.raises(ValueError):
         K.bias_act_bwd(dy[:m - 1], y[:m - 1], L.ACT_RELU, want_planes=True)
+
+
+def test_adam_step_with_device_step_counter(cuda):
+    """b2ctr_adam_step_dev + b2ctr_counter_add == b2ctr_adam_step with the step passed by value."""
+    K, L = _kern()
+    rng = np.random.RandomState(8)
+    n = 5000
+    w0, g = _r(rng, n), _r(rng, n)
+    wa, wb = w0.to(cuda), w0.to(cuda)
+    ma, va = torch.zeros(n, device=cuda), torch.zeros(n, device=cuda)
+    mb, vb = torch.zeros(n, device=cuda), torch.zeros(n, device=cuda)
+    ctr = torch.zeros(1, dtype=torch.int64, device=cuda)
+    for step in range(1, 6):
+        gs = (g * step).to(cuda)
+        K.adam_step(wa, gs, ma, va, 1e-3, step, l2=1e-4)
+        K.counter_add(ctr, 1)
+        K.adam_step_dev(wb, gs, mb, vb, 1e-3, ctr, l2=1e-4)
+        assert int(ctr.item()) == step
+        torch.testing.assert_close(wb, wa, rtol=1e-6, atol=1e-8)
+    assert torch.equal(ma, mb) and torch.equal(va, vb)

@@ -143,3 +143,31 @@ def test_training_step_graph_replay_matches_eager(cuda):
     md.compile(SGD(0.05), "binary_crossentropy")
     md.fit(x, y, batch_size=bs, epochs=1, shuffle=False, verbose=0)
     assert not md._step_graphs
+
+
+def test_adam_training_is_graph_replayed_and_matches_eager(cuda):
+    """Adam keeps its step count on the device (b2ctr_adam_step_dev), so the default optimizer of the reference's
+    examples is replayed as a step graph too; dense (Keras) embedding updates."""
+    import numpy as np
+    from deepctr_b200.models import DeepFM
+    from deepctr_b200.feature_column import SparseFeat, DenseFeat
+    cols = [SparseFeat("C%d" % i, 40 + i, 8) for i in range(4)] + [DenseFeat("I%d" % i, 1) for i in range(2)]
+    rng = np.random.RandomState(5)
+    n, bs = 64 * 8, 64
+    x = {"C%d" % i: rng.randint(0, 40 + i, n).astype(np.int32) for i in range(4)}
+    x.update({"I%d" % i: rng.rand(n).astype(np.float32) for i in range(2)})
+    y = rng.randint(0, 2, n).astype(np.float32)
+    hist, w0 = {}, None
+    for mode in ("off", "auto"):
+        m = DeepFM(cols, cols, dnn_hidden_units=(16, 8), seed=3)
+        m.compile("adam", "binary_crossentropy", step_graph=mode)
+        if w0 is None:
+            w0 = [w.copy() for w in m.get_weights()]
+        else:
+            m.set_weights(w0)
+        h = m.fit(x, y, batch_size=bs, epochs=2, shuffle=False, verbose=0)
+        hist[mode] = (h.history["loss"], m)
+    assert len(hist["auto"][1]._step_graphs) == 3 and not hist["off"][1]._step_graphs
+    np.testing.assert_allclose(hist["auto"][0], hist["off"][0], rtol=2e-5)
+    for wa, wo in zip(hist["auto"][1].weights, hist["off"][1].weights):
+        np.testing.assert_allclose(wa.value(), wo.value(), rtol=1e-4, atol=1e-6)

@@ -436,7 +436,7 @@ def main():
         (max(cands, key=lambda r: r["avg_launch_ms"]) if cands else None)
 
     cpu = None
-    if not args.no_cpu_baseline:
+    if not args.no_cpu_baseline and world == 1:      # rank 0 at N = 1 only (the N > 1 lines carry null)
         sb = min(args.cpu_sample_batch, cfg["batch"])
         v, cms, threads = run_cpu(cfg, 4, 1, sb)
         cpu = {"value": v, "unit": "samples/s", "cores": threads, "kind": "port",

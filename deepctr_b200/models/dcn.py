@@ -1,40 +1,23 @@
-"""Deep & Cross Network builder - drop-in for deepctr/models/dcn.py:22-78.
-Model inputs come from dnn_feature_columns only (dcn.py:48), as in the reference."""
-from ..engine import Model, Dense, Concatenate
-from ..feature_column import build_input_features, get_linear_logit, input_from_feature_columns
-from ..layers.core import PredictionLayer, DNN
+"""Deep & Cross Network (Wang et al. 2017 / 2020) - drop-in for the reference builder
+deepctr/models/dcn.py:22-78.  As there, the model's inputs are those of `dnn_feature_columns` only (:48)."""
+from ..engine import Concatenate
 from ..layers.interaction import CrossNet
-from ..layers.utils import add_func, combined_dnn_input
+from ._tower import Tower, total
 
 
 def DCN(linear_feature_columns, dnn_feature_columns, cross_num=2, cross_parameterization='vector',
         dnn_hidden_units=(256, 128, 64), l2_reg_linear=1e-5, l2_reg_embedding=1e-5, l2_reg_cross=1e-5,
         l2_reg_dnn=0, seed=1024, dnn_dropout=0, dnn_use_bn=False, dnn_activation='relu', task='binary'):
-    if len(dnn_hidden_units) == 0 and cross_num == 0:
+    has_deep, has_cross = len(dnn_hidden_units) > 0, cross_num > 0
+    if not has_deep and not has_cross:
         raise ValueError("Either hidden_layer or cross layer must > 0")
-
-    features = build_input_features(dnn_feature_columns)
-    inputs_list = list(features.values())
-    linear_logit = get_linear_logit(features, linear_feature_columns, seed=seed, prefix='linear',
-                                    l2_reg=l2_reg_linear)
-    emb_list, dense_value_list = input_from_feature_columns(features, dnn_feature_columns,
-                                                            l2_reg_embedding, seed)
-    dnn_input = combined_dnn_input(emb_list, dense_value_list)
-
-    def deep():
-        return DNN(dnn_hidden_units, dnn_activation, l2_reg_dnn, dnn_dropout, dnn_use_bn, seed=seed)(dnn_input)
-
-    def cross():
-        return CrossNet(cross_num, parameterization=cross_parameterization, l2_reg=l2_reg_cross)(dnn_input)
-
-    if len(dnn_hidden_units) > 0 and cross_num > 0:
-        deep_out = deep()
-        stack = Concatenate()([cross(), deep_out])
-    elif len(dnn_hidden_units) > 0:
-        stack = deep()
-    elif cross_num > 0:
-        stack = cross()
-    else:
-        raise NotImplementedError
-    final_logit = add_func([Dense(1, use_bias=False)(stack), linear_logit])
-    return Model(inputs=inputs_list, outputs=PredictionLayer(task)(final_logit))
+    t = Tower(dnn_feature_columns, linear_feature_columns, dnn_feature_columns, seed, l2_reg_linear,
+              l2_reg_embedding)
+    x0 = t.flat_input()
+    branches = []
+    if has_deep:
+        branches.append(t.mlp(dnn_hidden_units, dnn_activation, l2_reg_dnn, dnn_dropout, dnn_use_bn))
+    if has_cross:
+        branches.insert(0, CrossNet(cross_num, parameterization=cross_parameterization, l2_reg=l2_reg_cross)(x0))
+    stack = Concatenate()(branches) if len(branches) == 2 else branches[0]
+    return t.finish(total([t.project(stack), t.linear_logit]), task)

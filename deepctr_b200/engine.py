@@ -2,7 +2,8 @@
 
 What the reference gets from TensorFlow/Keras (symbolic ``Input``s, the ``Layer`` protocol, the
 functional ``Model`` with compile/fit/predict, automatic differentiation, optimizers) is provided
-here in ~one file so that the reference's builder bodies (deepctr/models/*.py) run unchanged:
+here in ~one file, so that builders with the reference's signatures (deepctr_b200/models/) and layers with
+its Keras protocol (deepctr_b200/layers/) have a runtime:
 
 * ``Var``      - a device buffer (torch tensor used purely as memory handle) + gradient + Keras mask.
                  A Var can be a column WINDOW of a wider per-sample buffer (``base``/``col0``) - that is

@@ -486,8 +486,23 @@ def _shape_of(x):
 _name_counts = {}
 
 
+def clear_session():
+    """tf.keras.backend.clear_session(): reset the per-class counters behind automatic layer names, so the
+    next model built in this process is named like the first one (``dnn``, ``dense``, ``dense_1`` ...)."""
+    _name_counts.clear()
+
+
+def _snake_case(cls):
+    """Keras' automatic layer name for a class (``DNN`` -> ``dnn``, ``CrossNet`` -> ``cross_net``,
+    ``_Add`` -> ``private__add``): weight names ``<layer>/<weight>`` then line up with the reference's."""
+    import re
+    s = re.sub("(.)([A-Z][a-z0-9]+)", r"\1_\2", cls)
+    s = re.sub("([a-z])([A-Z])", r"\1_\2", s).lower()
+    return "private" + s if s.startswith("_") else s
+
+
 def _auto_name(cls):
-    base = "".join(["_" + c.lower() if c.isupper() and i else c.lower() for i, c in enumerate(cls)])
+    base = _snake_case(cls)
     n = _name_counts.get(base, 0)
     _name_counts[base] = n + 1
     return base if n == 0 else "%s_%d" % (base, n)
@@ -532,6 +547,11 @@ class Layer(object):
         return w
 
     def _track(self, layer):
+        """Register a nested layer (its weights are addressed ``<this layer>/<attribute path>/<weight>``).
+        Keras draws automatic names from one counter per class whether a layer is nested or not, so the
+        nested layer consumes its class' next name too: in DIN the attention unit's inner DNN takes ``dnn``
+        and the tower's DNN is ``dnn_1``, as in the reference."""
+        _auto_name(layer.__class__.__name__)
         self._sublayers.append(layer)
         return layer
 

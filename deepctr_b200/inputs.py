@@ -100,158 +100,139 @@ def _grad_target(w, opt_ctx):
 
 
 # ================================================================================================
-# reference-compatible functions
+# the deepctr/inputs.py function surface (same names, arguments and return structures; bodies are
+# this package's own: one table registry + one id resolver shared by every lookup flavour)
 # ================================================================================================
-def _create_embedding_layer(feat, l2_reg, prefix, name_suffix, mask_zero=False):
-    """deepctr/inputs.py:19-26."""
-    emb = Embedding(feat.vocabulary_size, feat.embedding_dim,
-                    embeddings_initializer=feat.embeddings_initializer,
-                    embeddings_regularizer=l2(l2_reg),
-                    name=prefix + '_' + name_suffix + '_' + feat.embedding_name,
-                    mask_zero=mask_zero, trainable=feat.trainable)
-    return emb
+_SHARED_ATTRS = ('vocabulary_size', 'embedding_dim', 'trainable')
 
 
 def _check_embedding_compatible(embedding_name, existing_feat, feat):
-    """deepctr/inputs.py:29-37 (same message)."""
-    for attr in ('vocabulary_size', 'embedding_dim', 'trainable'):
-        if getattr(existing_feat, attr) != getattr(feat, attr):
-            raise ValueError(
-                "Feature columns with the same embedding_name must share the same "
-                "{}. embedding_name='{}' has {} and {}.".format(
-                    attr, embedding_name, getattr(existing_feat, attr), getattr(feat, attr)))
+    """Columns sharing an ``embedding_name`` share ONE table, so they must agree on its geometry
+    (deepctr/inputs.py:29-37; the message is part of the interface, tests/feature_test.py:53-60)."""
+    clash = [a for a in _SHARED_ATTRS if getattr(existing_feat, a) != getattr(feat, a)]
+    if clash:
+        a = clash[0]
+        raise ValueError("Feature columns with the same embedding_name must share the same "
+                         "{}. embedding_name='{}' has {} and {}.".format(
+                             a, embedding_name, getattr(existing_feat, a), getattr(feat, a)))
 
 
-def get_inputs_list(inputs):
-    return list(chain(*list(map(lambda x: x.values(), filter(lambda x: x is not None, inputs)))))
+class _TableRegistry(object):
+    """embedding_name -> Embedding layer, first declaration wins (deepctr/inputs.py:44-71)."""
+
+    def __init__(self, l2_reg, prefix):
+        self.l2_reg, self.prefix = l2_reg, prefix
+        self.tables, self.owner = {}, {}
+
+    def declare(self, feat, kind, mask_zero):
+        key = feat.embedding_name
+        if key in self.tables:
+            _check_embedding_compatible(key, self.owner[key], feat)
+            return
+        self.owner[key] = feat
+        self.tables[key] = Embedding(feat.vocabulary_size, feat.embedding_dim,
+                                     embeddings_initializer=feat.embeddings_initializer,
+                                     embeddings_regularizer=l2(self.l2_reg),
+                                     name="%s_%s_%s" % (self.prefix, kind, key),      # inputs.py:23
+                                     mask_zero=mask_zero, trainable=feat.trainable)
 
 
 def create_embedding_dict(sparse_feature_columns, varlen_sparse_feature_columns, seed, l2_reg,
                           prefix='sparse_', seq_mask_zero=True):
-    """deepctr/inputs.py:44-71: one table per distinct embedding_name; mask_zero when shared with /
-    owned by a VarLen column."""
-    sparse_embedding = {}
-    embedding_feature_dict = {}
-    varlen_names = set(f.embedding_name for f in varlen_sparse_feature_columns) \
-        if varlen_sparse_feature_columns else set()
+    """One table per distinct embedding_name.  A table is ``mask_zero`` when a VarLen column reads it
+    (its own ``seq_emb`` table, or a SparseFeat table it shares: DIN's item_id / hist_item_id)."""
+    varlen = list(varlen_sparse_feature_columns or ())
+    read_by_sequences = set(f.embedding_name for f in varlen)
+    reg = _TableRegistry(l2_reg, prefix)
     for feat in sparse_feature_columns:
-        name = feat.embedding_name
-        if name in sparse_embedding:
-            _check_embedding_compatible(name, embedding_feature_dict[name], feat)
-            continue
-        mask_zero = seq_mask_zero and name in varlen_names
-        sparse_embedding[name] = _create_embedding_layer(feat, l2_reg, prefix, 'emb', mask_zero)
-        embedding_feature_dict[name] = feat
-    if varlen_sparse_feature_columns:
-        for feat in varlen_sparse_feature_columns:
-            name = feat.embedding_name
-            if name in sparse_embedding:
-                _check_embedding_compatible(name, embedding_feature_dict[name], feat)
-                continue
-            sparse_embedding[name] = _create_embedding_layer(feat, l2_reg, prefix, 'seq_emb', seq_mask_zero)
-            embedding_feature_dict[name] = feat
-    return sparse_embedding
+        reg.declare(feat, 'emb', bool(seq_mask_zero and feat.embedding_name in read_by_sequences))
+    for feat in varlen:
+        reg.declare(feat, 'seq_emb', seq_mask_zero)
+    return reg.tables
 
 
 def create_embedding_matrix(feature_columns, l2_reg, seed, prefix="", seq_mask_zero=True):
     from . import feature_column as fc_lib
-    sparse = [x for x in feature_columns if isinstance(x, fc_lib.SparseFeat)] if feature_columns else []
-    varlen = [x for x in feature_columns if isinstance(x, fc_lib.VarLenSparseFeat)] if feature_columns else []
-    return create_embedding_dict(sparse, varlen, seed, l2_reg, prefix=prefix + 'sparse',
-                                 seq_mask_zero=seq_mask_zero)
+    cols = list(feature_columns or ())
+    return create_embedding_dict([c for c in cols if isinstance(c, fc_lib.SparseFeat)],
+                                 [c for c in cols if isinstance(c, fc_lib.VarLenSparseFeat)],
+                                 seed, l2_reg, prefix=prefix + 'sparse', seq_mask_zero=seq_mask_zero)
 
 
-def _hash_layer(fc, mask_zero):
+def _ids_of(fc, tensor, mask_zero):
+    """The id tensor a column looks up: the input itself, or Hash(...)(input) for ``use_hash`` columns
+    (folded into the gather kernel / the Feeder by the planner whenever the input is a model input)."""
+    if not fc.use_hash:
+        return tensor
     from .layers.utils import Hash
-    return Hash(fc.vocabulary_size, mask_zero=mask_zero, vocabulary_path=fc.vocabulary_path)
+    return Hash(fc.vocabulary_size, mask_zero=mask_zero, vocabulary_path=fc.vocabulary_path)(tensor)
+
+
+def _selected(columns, return_feat_list):
+    keep = set(return_feat_list)
+    return [fc for fc in columns if not keep or fc.name in keep]
+
+
+def get_inputs_list(inputs):
+    return [t for d in inputs if d is not None for t in d.values()]
 
 
 def get_embedding_vec_list(embedding_dict, input_dict, sparse_feature_columns, return_feat_list=(),
                            mask_feat_list=()):
-    vecs = []
-    for fg in sparse_feature_columns:
-        name = fg.name
-        if len(return_feat_list) == 0 or name in return_feat_list:
-            idx = _hash_layer(fg, name in mask_feat_list)(input_dict[name]) if fg.use_hash else input_dict[name]
-            vecs.append(embedding_dict[name](idx))
-    return vecs
+    """Legacy flavour (inputs.py:74-86): tables keyed by FEATURE name, flat list out."""
+    return [embedding_dict[fc.name](_ids_of(fc, input_dict[fc.name], fc.name in mask_feat_list))
+            for fc in _selected(sparse_feature_columns, return_feat_list)]
 
 
 def embedding_lookup(sparse_embedding_dict, sparse_input_dict, sparse_feature_columns, return_feat_list=(),
                      mask_feat_list=(), to_list=False):
-    """deepctr/inputs.py:101-117."""
-    group_embedding_dict = defaultdict(list)
-    for fc in sparse_feature_columns:
-        feature_name, embedding_name = fc.name, fc.embedding_name
-        if len(return_feat_list) == 0 or feature_name in return_feat_list:
-            if fc.use_hash:
-                lookup_idx = _hash_layer(fc, feature_name in mask_feat_list)(sparse_input_dict[feature_name])
-            else:
-                lookup_idx = sparse_input_dict[feature_name]
-            group_embedding_dict[fc.group_name].append(sparse_embedding_dict[embedding_name](lookup_idx))
-    if to_list:
-        return list(chain.from_iterable(group_embedding_dict.values()))
-    return group_embedding_dict
+    """[B,1,E] (or [B,T,E]) per selected column, grouped by ``group_name`` (inputs.py:101-117)."""
+    groups = defaultdict(list)
+    for fc in _selected(sparse_feature_columns, return_feat_list):
+        ids = _ids_of(fc, sparse_input_dict[fc.name], fc.name in mask_feat_list)
+        groups[fc.group_name].append(sparse_embedding_dict[fc.embedding_name](ids))
+    return [t for g in groups.values() for t in g] if to_list else groups
 
 
 def varlen_embedding_lookup(embedding_dict, sequence_input_dict, varlen_sparse_feature_columns):
-    """deepctr/inputs.py:120-130."""
-    out = {}
-    for fc in varlen_sparse_feature_columns:
-        if fc.use_hash:
-            lookup_idx = _hash_layer(fc, True)(sequence_input_dict[fc.name])
-        else:
-            lookup_idx = sequence_input_dict[fc.name]
-        out[fc.name] = embedding_dict[fc.embedding_name](lookup_idx)
-    return out
+    """feature name -> [B,T,E] (hashing always keeps 0 as the padding id; inputs.py:120-130)."""
+    return {fc.name: embedding_dict[fc.embedding_name](_ids_of(fc, sequence_input_dict[fc.name], True))
+            for fc in varlen_sparse_feature_columns}
 
 
 def get_varlen_pooling_list(embedding_dict, features, varlen_sparse_feature_columns, to_list=False):
-    """deepctr/inputs.py:133-158."""
+    """Pool every sequence to [B,1,E]: validity comes from ``length_name`` when the column has one,
+    else from the Keras mask of its mask_zero table; an optional per-position weight is applied first
+    (inputs.py:133-158).  The planner folds these chains into the fused gather."""
     from .layers.sequence import SequencePoolingLayer, WeightedSequenceLayer
-    pooling_vec_list = defaultdict(list)
+    groups = defaultdict(list)
     for fc in varlen_sparse_feature_columns:
-        name, combiner, length_name = fc.name, fc.combiner, fc.length_name
-        if length_name is not None:
-            if fc.weight_name is not None:
-                seq_input = WeightedSequenceLayer(weight_normalization=fc.weight_norm)(
-                    [embedding_dict[name], features[length_name], features[fc.weight_name]])
-            else:
-                seq_input = embedding_dict[name]
-            vec = SequencePoolingLayer(combiner, supports_masking=False)([seq_input, features[length_name]])
-        else:
-            if fc.weight_name is not None:
-                seq_input = WeightedSequenceLayer(weight_normalization=fc.weight_norm, supports_masking=True)(
-                    [embedding_dict[name], features[fc.weight_name]])
-            else:
-                seq_input = embedding_dict[name]
-            vec = SequencePoolingLayer(combiner, supports_masking=True)(seq_input)
-        pooling_vec_list[fc.group_name].append(vec)
-    if to_list:
-        return chain.from_iterable(pooling_vec_list.values())
-    return pooling_vec_list
+        by_length = fc.length_name is not None
+        extent = [features[fc.length_name]] if by_length else []
+        seq = embedding_dict[fc.name]
+        if fc.weight_name is not None:
+            seq = WeightedSequenceLayer(weight_normalization=fc.weight_norm, supports_masking=not by_length)(
+                [seq] + extent + [features[fc.weight_name]])
+        pool = SequencePoolingLayer(fc.combiner, supports_masking=not by_length)
+        groups[fc.group_name].append(pool([seq] + extent if by_length else seq))
+    return chain.from_iterable(groups.values()) if to_list else groups
 
 
 def get_dense_input(features, feature_columns):
-    """deepctr/inputs.py:161-172."""
     from . import feature_column as fc_lib
-    dense_cols = [x for x in feature_columns if isinstance(x, fc_lib.DenseFeat)] if feature_columns else []
     out = []
-    for fc in dense_cols:
-        if fc.transform_fn is None:
-            out.append(features[fc.name])
-        else:
-            out.append(E.Lambda(fc.transform_fn)(features[fc.name]))
+    for fc in (c for c in (feature_columns or ()) if isinstance(c, fc_lib.DenseFeat)):
+        t = features[fc.name]
+        out.append(t if fc.transform_fn is None else E.Lambda(fc.transform_fn)(t))
     return out
 
 
 def mergeDict(a, b):
-    c = defaultdict(list)
-    for k, v in a.items():
-        c[k].extend(v)
-    for k, v in b.items():
-        c[k].extend(v)
-    return c
+    merged = defaultdict(list)
+    for d in (a, b):
+        for k, v in d.items():
+            merged[k].extend(v)
+    return merged
 
 
 # ================================================================================================

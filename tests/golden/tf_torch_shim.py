@@ -10,6 +10,15 @@ and are stated as unpinned in DESIGN.md.
 
 ``install()`` registers the fake modules in sys.modules and loads ``deepctr.layers`` from the
 reference tree without running ``deepctr/__init__.py`` (which would start a thread that calls PyPI).
+
+Round 2: the Keras functional surface the reference's COMPOSITION code needs (``Input``, ``Embedding``
+with ``mask_zero``, ``Dense``, ``Lambda``, ``Concatenate``, ``Flatten``, ``Add``, ``Model``) is real
+now, executed EAGERLY: ``Input(name=...)`` returns the batch that ``CTX.feed`` holds for that name, so
+calling an unmodified builder (``deepctr.models.DeepFM(...)``) runs the reference's own
+``feature_column.py`` / ``inputs.py`` / builder body on that batch and ``Model.outputs`` is the result.
+``Layer.__call__`` follows tf.keras' implicit-mask protocol (``_keras_mask`` on tensors, ``mask=``
+injected when ``call`` accepts it, ``compute_mask`` after the call, identity copy when a layer
+returns its input) - that is what DIN's attention and the mask-based pooling layers consume.
 """
 import importlib
 import sys
@@ -293,6 +302,47 @@ class l2(object):
         self.l2 = l2
 
 
+# ---- eager-execution context ---------------------------------------------------------------------------
+class _Ctx(object):
+    """feed: Input name -> numpy batch; training: value injected into ``call(training=...)``;
+    rng/grad: when rng is set every add_weight draws O(1) values from it (so that zero-initialised
+    terms carry signal) and, with grad, the weights are autograd leaves; layers: creation-ordered
+    registry; depth: >0 while inside another layer's build/call (nested layers)."""
+
+    def __init__(self):
+        self.reset()
+
+    def reset(self):
+        self.feed, self.training, self.rng, self.grad, self.scale = {}, None, None, False, 1.0
+        self.layers, self.uid, self.depth = [], {}, 0
+
+
+CTX = _Ctx()
+
+
+def to_snake_case(name):
+    """keras.utils.generic_utils.to_snake_case (public Keras behaviour)."""
+    import re
+    s1 = re.sub("(.)([A-Z][a-z0-9]+)", r"\1_\2", name)
+    s2 = re.sub("([a-z])([A-Z])", r"\1_\2", s1).lower()
+    return "private" + s2 if s2[0] == "_" else s2
+
+
+def _unique_name(base):
+    n = CTX.uid.get(base, 0)
+    CTX.uid[base] = n + 1
+    return base if n == 0 else "%s_%d" % (base, n)
+
+
+def _flat(x):
+    if isinstance(x, (list, tuple)):
+        out = []
+        for e in x:
+            out.extend(_flat(e))
+        return out
+    return [x]
+
+
 # ---- keras layers ------------------------------------------------------------------------------------
 def _shape_of(x):
     if isinstance(x, (list, tuple)):
@@ -302,16 +352,30 @@ def _shape_of(x):
 
 class Layer(object):
     def __init__(self, name=None, trainable=True, dtype=None, **kwargs):
-        self.name = name or self.__class__.__name__.lower()
+        self.name = name or _unique_name(to_snake_case(self.__class__.__name__))
         self.built = False
+        self.trainable = trainable
         self._w = []
+        self._nested = CTX.depth > 0
+        CTX.layers.append(self)
         if not hasattr(self, "supports_masking"):
             self.supports_masking = False
 
     def add_weight(self, name=None, shape=None, dtype=None, initializer=None, regularizer=None,
                    trainable=True, **kw):
-        init = initializer() if isinstance(initializer, type) else (initializer or Zeros())
-        t = init(tuple(int(s) for s in shape)).float()
+        shape = tuple(int(s) for s in shape)
+        if CTX.rng is not None:
+            # O(1) values instead of the requested initialiser (zeros / 1e-4): every term carries signal
+            if name == "embeddings" or len(shape) < 2:
+                std = 0.3 if name == "embeddings" else 0.1
+            else:
+                std = 1.0 / np.sqrt(float(np.prod(shape[:-1])))
+            t = torch.as_tensor(CTX.rng.normal(0, std * CTX.scale, size=shape).astype(np.float32))
+        else:
+            init = initializer() if isinstance(initializer, type) else (initializer or Zeros())
+            t = init(shape).float()
+        if CTX.grad and trainable:
+            t.requires_grad_(True)
         self._w.append((name, t))
         return t
 
@@ -323,10 +387,45 @@ class Layer(object):
         self.built = True
 
     def __call__(self, inputs, **kwargs):
-        if not self.built:
-            self.build(_shape_of(inputs))
-            self.built = True
-        return self.call(inputs, **kwargs)
+        import inspect
+        CTX.depth += 1
+        try:
+            if not self.built:
+                self.build(_shape_of(inputs))
+                self.built = True
+            try:
+                params = inspect.signature(self.call).parameters
+            except (TypeError, ValueError):
+                params = {}
+            expects_mask = "mask" in params
+            explicit_cm = type(self).compute_mask is not Layer.compute_mask
+            # tf.keras base_layer._get_input_masks
+            input_masks = None
+            if self.supports_masking or expects_mask:
+                if kwargs.get("mask") is not None:
+                    input_masks = kwargs["mask"]
+                else:
+                    ms = [getattr(t, "_keras_mask", None) for t in _flat(inputs)]
+                    if any(m is not None for m in ms):
+                        input_masks = ms if isinstance(inputs, (list, tuple)) else ms[0]
+                        if expects_mask:
+                            kwargs["mask"] = input_masks
+            if "training" in params and "training" not in kwargs and CTX.training is not None:
+                kwargs["training"] = CTX.training
+            out = self.call(inputs, **kwargs)
+            # a layer that returns its input gets an identity copy (Keras wraps it in tf.identity)
+            if isinstance(out, torch.Tensor) and any(out is t for t in _flat(inputs)):
+                out = out.view_as(out)
+            # tf.keras base_layer._set_mask_metadata
+            if (self.supports_masking or explicit_cm) and isinstance(out, torch.Tensor) \
+                    and getattr(out, "_keras_mask", None) is None:
+                om = self.compute_mask(inputs, input_masks)
+                if om is not None:
+                    out._keras_mask = om
+            self._last_in, self._last_out = inputs, out
+            return out
+        finally:
+            CTX.depth -= 1
 
     def call(self, inputs, **kwargs):
         return inputs
@@ -365,7 +464,11 @@ class BatchNormalization(Layer):
     def call(self, x, training=None, **kwargs):
         n = x.shape[-1]
         if self.moving_mean is None:
-            self.moving_mean, self.moving_variance = torch.zeros(n), torch.ones(n)
+            if CTX.rng is not None:
+                self.moving_mean = torch.as_tensor(CTX.rng.normal(0, 0.2, size=n).astype(np.float32))
+                self.moving_variance = torch.as_tensor(np.abs(CTX.rng.normal(1.0, 0.2, size=n)).astype(np.float32))
+            else:
+                self.moving_mean, self.moving_variance = torch.zeros(n), torch.ones(n)
         if training:
             red = tuple(range(x.dim() - 1))
             mean, var = x.mean(dim=red), x.var(dim=red, unbiased=False)
@@ -381,8 +484,15 @@ class Flatten(Layer):
 
 class Add(Layer):
     def call(self, xs, **kw):
-        out = xs[0]
-        for x in xs[1:]:
+        # keras.layers.merge._Merge.call: lower-rank operands are expanded at axis 1 up to the max rank
+        nd = max(x.dim() for x in xs)
+        ys = []
+        for x in xs:
+            while x.dim() < nd:
+                x = x.unsqueeze(1)
+            ys.append(x)
+        out = ys[0]
+        for x in ys[1:]:
             out = out + x
         return out
 
@@ -390,6 +500,96 @@ class Add(Layer):
 class _Dummy(Layer):
     def __init__(self, *a, **kw):
         Layer.__init__(self)
+
+
+def Input(shape=None, name=None, dtype=None, **kw):
+    """Eager stand-in for tf.keras.layers.Input: the batch CTX.feed holds under ``name``, shaped
+    [B] + shape and cast to ``dtype``."""
+    if name not in CTX.feed:
+        raise KeyError("no data fed for Input %r" % (name,))
+    a = np.asarray(CTX.feed[name])
+    shape = (shape,) if isinstance(shape, int) else tuple(shape)
+    dt = as_dtype(dtype or "float32")
+    if dt == string:
+        t = constant(a.reshape((a.shape[0],) + shape))
+    else:
+        t = torch.as_tensor(a.reshape((a.shape[0],) + shape)).to(dt.torch)
+    t._keras_input_name = name
+    return t
+
+
+class Embedding(Layer):
+    def __init__(self, input_dim, output_dim, embeddings_initializer=None, embeddings_regularizer=None,
+                 mask_zero=False, name=None, **kw):
+        Layer.__init__(self, name=name)
+        self.input_dim, self.output_dim, self.mask_zero = int(input_dim), int(output_dim), mask_zero
+        self.supports_masking = mask_zero
+        self.embeddings_initializer = embeddings_initializer
+        self.embeddings_regularizer = embeddings_regularizer
+
+    def build(self, input_shape):
+        self.embeddings = self.add_weight(name="embeddings", shape=(self.input_dim, self.output_dim),
+                                          initializer=self.embeddings_initializer)
+        self.built = True
+
+    def call(self, inputs, **kw):
+        idx = inputs.to(torch.int64)
+        if idx.numel() and (int(idx.min()) < 0 or int(idx.max()) >= self.input_dim):
+            raise IndexError("InvalidArgument: indices out of range [0, %d)" % self.input_dim)   # TF-CPU behaviour
+        return self.embeddings[idx]
+
+    def compute_mask(self, inputs, mask=None):
+        if not self.mask_zero:
+            return None
+        return inputs != 0
+
+
+class Dense(Layer):
+    def __init__(self, units, activation=None, use_bias=True, kernel_initializer=None, name=None, **kw):
+        Layer.__init__(self, name=name)
+        self.units, self.activation, self.use_bias = int(units), activation, use_bias
+        self.kernel_initializer = kernel_initializer
+        self.supports_masking = True
+
+    def build(self, input_shape):
+        self.kernel = self.add_weight(name="kernel", shape=(int(input_shape[-1]), self.units),
+                                      initializer=self.kernel_initializer or glorot_uniform())
+        self.bias = self.add_weight(name="bias", shape=(self.units,), initializer=Zeros()) if self.use_bias else None
+        self.built = True
+
+    def call(self, inputs, **kw):
+        y = torch.matmul(inputs, self.kernel)
+        if self.bias is not None:
+            y = y + self.bias
+        return {None: lambda v: v, "linear": lambda v: v, "relu": torch.relu, "sigmoid": torch.sigmoid,
+                "tanh": torch.tanh}[self.activation](y)
+
+
+class Lambda(Layer):
+    def __init__(self, function, name=None, **kw):
+        Layer.__init__(self, name=name)
+        self.function = function
+
+    def call(self, inputs, **kw):
+        return self.function(inputs)
+
+
+class Concatenate(Layer):
+    def __init__(self, axis=-1, name=None, **kw):
+        Layer.__init__(self, name=name)
+        self.axis = axis
+
+    def call(self, inputs, **kw):
+        return torch.cat(list(inputs), dim=self.axis)
+
+
+class Model(object):
+    """tf.keras.models.Model of an eagerly executed graph: holds the already computed outputs and
+    the creation-ordered layer registry of this build."""
+
+    def __init__(self, inputs=None, outputs=None, name=None):
+        self.inputs, self.outputs, self.name = inputs, outputs, name
+        self.layers = list(CTX.layers)
 
 
 # ---- lookup ops --------------------------------------------------------------------------------------
@@ -442,12 +642,14 @@ def install(reference_root="/root/reference"):
              all=lambda x, axis=None, keepdims=False: torch.all(x, dim=axis, keepdim=keepdims),
              batch_dot=None)
     layers = _mod("tensorflow.keras.layers", Layer=Layer, Activation=Activation, Dropout=Dropout,
-                  BatchNormalization=BatchNormalization, Flatten=Flatten, Add=Add, Lambda=_Dummy, Dense=_Dummy,
-                  Conv2D=_Dummy, MaxPooling2D=_Dummy, LSTM=_Dummy, Embedding=_Dummy, Input=_Dummy)
+                  BatchNormalization=BatchNormalization, Flatten=Flatten, Add=Add, Lambda=Lambda, Dense=Dense,
+                  Concatenate=Concatenate, Conv2D=_Dummy, MaxPooling2D=_Dummy, LSTM=_Dummy, Embedding=Embedding,
+                  Input=Input)
     inits = _mod("tensorflow.keras.initializers", RandomNormal=RandomNormal, Zeros=Zeros, Ones=Ones,
                  TruncatedNormal=TruncatedNormal, glorot_normal=glorot_normal, glorot_uniform=glorot_uniform)
     regs = _mod("tensorflow.keras.regularizers", l2=l2)
-    keras = _mod("tensorflow.keras", backend=K, layers=layers, initializers=inits, regularizers=regs)
+    models = _mod("tensorflow.keras.models", Model=Model)
+    keras = _mod("tensorflow.keras", backend=K, layers=layers, initializers=inits, regularizers=regs, models=models)
     tf.keras = keras
     py = _mod("tensorflow.python")
     ops = _mod("tensorflow.python.ops")
@@ -462,6 +664,11 @@ def install(reference_root="/root/reference"):
     pkg = types.ModuleType("deepctr")
     pkg.__path__ = [reference_root + "/deepctr"]
     sys.modules["deepctr"] = pkg
+    # the model packages, without their __init__ (it imports all 30 builders and their Keras symbols)
+    for n, sub in (("deepctr.models", "/deepctr/models"), ("deepctr.models.sequence", "/deepctr/models/sequence")):
+        mp = types.ModuleType(n)
+        mp.__path__ = [reference_root + sub]
+        sys.modules[n] = mp
     for n in ("deepctr.contrib", "deepctr.contrib.rnn", "deepctr.contrib.rnn_v2", "deepctr.contrib.utils"):
         m = _mod(n, dynamic_rnn=None, QAAttGRUCell=None, VecAttGRUCell=None)
         if n == "deepctr.contrib":

@@ -75,6 +75,7 @@ SIGNATURES = {
     "b2ctr_embed_gather_uniform_fwd": (_i32, [C.POINTER(UniformGather), _i64, _vp]),
     "b2ctr_embed_scatter_uniform_bwd": (_i32, [C.POINTER(UniformGather), _vp, _vp, _vp, _f32, _f32,
                                                _i64, _vp]),
+    "b2ctr_embed_oob_count": (_i32, [C.POINTER(C.c_int64), _i32, _vp]),
     "b2ctr_hash64": (_i32, [_vp, _i32, _i64, _i64, _i32, _vp, _vp]),
     "b2ctr_init_normal": (_i32, [_vp, _i64, _f32, _f32, _u64, _vp]),
     "b2ctr_gemm_workspace_bytes": (_sz, [C.POINTER(Gemm)]),

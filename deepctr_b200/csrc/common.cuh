@@ -33,6 +33,12 @@ inline void count_launch(int n = 1) { g_launches.fetch_add(n, std::memory_order_
 
 constexpr int kNumSMs = 148;  // B200: 2 dies x 74 SMs
 
+// Device counter of embedding ids outside [0, vocabulary_size) seen by the gather / scatter kernels of the
+// current device (one per device, allocated on first use, never freed).  Out-of-range ids read a ZERO row and
+// are skipped by the update kernels (TF-GPU semantics, memory-safe); the host reads the counter with
+// b2ctr_embed_oob_count and raises like TF-CPU does.
+unsigned long long* oob_counter();
+
 static inline int64_t ceil_div(int64_t a, int64_t b) { return (a + b - 1) / b; }
 
 // Grid for a grid-stride kernel: whole multiples of the SM count, capped by the work.
@@ -116,6 +122,11 @@ __device__ __forceinline__ void red_add_f4_pol(float* p, float4 v, uint64_t pol)
 __device__ __forceinline__ void red_add_f1_pol(float* p, float v, uint64_t pol) {
   asm volatile("red.relaxed.gpu.global.add.L2::cache_hint.f32 [%0], %1, %2;" ::"l"(p), "f"(v), "l"(pol)
                : "memory");
+}
+
+__device__ __forceinline__ bool id_in_range(int64_t id, int64_t vocab) { return (uint64_t)id < (uint64_t)vocab; }
+__device__ __forceinline__ void note_oob(unsigned long long* counter) {
+  if (counter) atomicAdd(counter, 1ull);
 }
 
 __device__ __forceinline__ float warp_sum(float v) {

@@ -113,6 +113,7 @@ __device__ __forceinline__ int64_t lookup_id(const b2ctr_feature_t& ft, int64_t 
 constexpr int kFeatChunk = 64;  // descriptors per launch (6 KB of kernel parameters)
 struct FeatBlock {
   b2ctr_feature_t f[kFeatChunk];
+  unsigned long long* oob;      // out-of-range id counter (common.cuh)
   int32_t nfeat;
 };
 
@@ -247,9 +248,11 @@ __global__ void __launch_bounds__(256)
       // plain lookup: T rows copied verbatim (padded positions read their real row; Keras masks later)
       for (int t = 0; t < T; ++t) {
         const int64_t id = lookup_id(ft, ibase + t);
-        const float* row = ft.table + id * dim;
+        const bool ok = id_in_range(id, ft.vocab);       // out-of-range id: zero row (+ counted)
+        if (!ok && lane == 0) note_oob(fb.oob);
+        const float* row = ft.table + (ok ? id : 0) * dim;
         for (int e = lane * VEC; e < dim; e += G * VEC)
-          vstore(out + (int64_t)t * dim + e, vload(row + e, (V*)nullptr));
+          vstore(out + (int64_t)t * dim + e, ok ? vload(row + e, (V*)nullptr) : vzero<VEC>());
       }
       continue;
     }
@@ -273,7 +276,9 @@ __global__ void __launch_bounds__(256)
         for (int u = 0; u < 4; ++u) {
           // max pooling reads masked rows too (x - 1e9 competes, sequence.py:97-98)
           const bool need = t0 + u < T && (val[u] || ft.pool == B2CTR_POOL_MAX);
-          x[u] = need ? vload(ft.table + id[u] * dim + e, (V*)nullptr) : vzero<VEC>();
+          const bool ok = id_in_range(id[u], ft.vocab);
+          if (need && !ok && e == 0) note_oob(fb.oob);      // e == 0 <=> lane 0, first pass
+          x[u] = (need && ok) ? vload(ft.table + id[u] * dim + e, (V*)nullptr) : vzero<VEC>();
         }
 #pragma unroll
         for (int u = 0; u < 4; ++u) {
@@ -314,6 +319,7 @@ __global__ void __launch_bounds__(256)
     if (ft.pool == B2CTR_POOL_NONE) {
       for (int t = 0; t < T; ++t) {
         const int64_t id = lookup_id(ft, ibase + t);
+        if (!id_in_range(id, ft.vocab)) continue;          // never write outside the table
         float* row = ft.table + id * dim;
         for (int e = lane * VEC; e < dim; e += G * VEC)
           vred(row + e, vmuls(vload(gout + (int64_t)t * dim + e, (V*)nullptr), scale));
@@ -339,7 +345,8 @@ __global__ void __launch_bounds__(256)
           for (int t = 0; t < T; ++t) {
             const int64_t id = lookup_id(ft, ibase + t);
             const bool valid = pos_valid(ft, t, id, len);
-            V xv = vload((ft.src_table ? ft.src_table : ft.table) + id * dim + e, (V*)nullptr);
+            const bool ok = id_in_range(id, ft.vocab);
+            V xv = ok ? vload((ft.src_table ? ft.src_table : ft.table) + id * dim + e, (V*)nullptr) : vzero<VEC>();
             const float w = pos_weight(ft, si, b, t, valid);
             if (ft.weight_mode != B2CTR_WEIGHT_NONE) xv = vmuls(xv, w);
             if (!valid) xv = vsubs(xv, 1e9f);
@@ -354,7 +361,7 @@ __global__ void __launch_bounds__(256)
             } else {
 #pragma unroll
               for (int i = 0; i < VEC; ++i)
-                if (xs[i] == mx[i]) red_add_f1(ft.table + id * dim + e + i, gv[i] / (float)cnt[i] * w);
+                if (xs[i] == mx[i] && ok) red_add_f1(ft.table + id * dim + e + i, gv[i] / (float)cnt[i] * w);
             }
           }
         }
@@ -363,7 +370,7 @@ __global__ void __launch_bounds__(256)
       for (int t = 0; t < T; ++t) {
         const int64_t id = lookup_id(ft, ibase + t);
         const bool valid = pos_valid(ft, t, id, len);
-        if (!valid) continue;
+        if (!valid || !id_in_range(id, ft.vocab)) continue;
         V gt = g;
         if (ft.weight_mode != B2CTR_WEIGHT_NONE) gt = vmuls(gt, pos_weight(ft, si, b, t, true));
         vred(ft.table + id * dim + e, gt);
@@ -381,6 +388,8 @@ struct UniParams {
   float* lin[kUniMaxFeat];
   const void* idx[kUniMaxFeat];
   int64_t idx_stride[kUniMaxFeat];
+  int64_t vocab[kUniMaxFeat];     // FULL vocabulary (also when the table is row-sharded): id validity
+  unsigned long long* oob;
   const float* dense;
   float* x;
   float* linear;
@@ -491,7 +500,10 @@ __global__ void __launch_bounds__(256, (SHARD || PLANES) ? 3 : 4)
         const int64_t idb = __shfl_sync(0xffffffffu, id1, fs & 31);
         const int64_t id = fs < 32 ? ida : idb;
         if (f < F) {
-          if (SHARD) {
+          if (!id_in_range(id, p.vocab[f])) {               // zero row, counted once per row
+            v[u] = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (chunk == 0) note_oob(p.oob);
+          } else if (SHARD) {
             v[u] = ld_peer_f4(shard_row(p.peer_tab, p, f, id, dim) + chunk * 4);
           } else {
             const float* src = p.table[f] + id * dim + chunk * 4;
@@ -530,12 +542,14 @@ __global__ void __launch_bounds__(256, (SHARD || PLANES) ? 3 : 4)
     if (p.linear != nullptr) {
       float l = 0.f;
       if (p.has_lin) {
+        const bool ok0 = lane < F && id_in_range(id0, p.vocab[lane]);
+        const bool ok1 = lane + 32 < F && id_in_range(id1, p.vocab[lane + 32 < F ? lane + 32 : 0]);
         if (SHARD) {
-          if (lane < F) l += ld_peer_f1(shard_row(p.peer_lin, p, lane, id0, 1));
-          if (lane + 32 < F) l += ld_peer_f1(shard_row(p.peer_lin, p, lane + 32, id1, 1));
+          if (ok0) l += ld_peer_f1(shard_row(p.peer_lin, p, lane, id0, 1));
+          if (ok1) l += ld_peer_f1(shard_row(p.peer_lin, p, lane + 32, id1, 1));
         } else {
-          if (lane < F) l += hints ? ldg_f1_pol(p.lin[lane] + id0, pol_keep) : p.lin[lane][id0];
-          if (lane + 32 < F) l += hints ? ldg_f1_pol(p.lin[lane + 32] + id1, pol_keep) : p.lin[lane + 32][id1];
+          if (ok0) l += hints ? ldg_f1_pol(p.lin[lane] + id0, pol_keep) : p.lin[lane][id0];
+          if (ok1) l += hints ? ldg_f1_pol(p.lin[lane + 32] + id1, pol_keep) : p.lin[lane + 32][id1];
         }
       }
       l = warp_sum(l);
@@ -628,7 +642,7 @@ __global__ void __launch_bounds__(256, SHARD ? 2 : 3)
         const int64_t ida = __shfl_sync(0xffffffffu, id0, fs & 31);
         const int64_t idb = __shfl_sync(0xffffffffu, id1, fs & 31);
         const int64_t id = fs < 32 ? ida : idb;
-        if (f < F) {
+        if (f < F && id_in_range(id, p.vocab[f])) {
           float4 r = g[u];
           if (dfm && ((p.fm_mask >> f) & 1ull)) {
             r.x += gfm * (s.x - xv[u].x);
@@ -646,15 +660,17 @@ __global__ void __launch_bounds__(256, SHARD ? 2 : 3)
     }
     if (dlinear && p.has_lin) {
       const float gl = dlinear[b] * lin_scale;
+      const bool ok0 = lane < F && id_in_range(id0, p.vocab[lane]);
+      const bool ok1 = lane + 32 < F && id_in_range(id1, p.vocab[lane + 32 < F ? lane + 32 : 0]);
       if (SHARD) {
-        if (lane < F) red_peer_f1(shard_row(p.peer_lin, p, lane, id0, 1), gl);
-        if (lane + 32 < F) red_peer_f1(shard_row(p.peer_lin, p, lane + 32, id1, 1), gl);
+        if (ok0) red_peer_f1(shard_row(p.peer_lin, p, lane, id0, 1), gl);
+        if (ok1) red_peer_f1(shard_row(p.peer_lin, p, lane + 32, id1, 1), gl);
       } else if (p.store_grads) {
-        if (lane < F) p.lin[lane][id0] = gl;
-        if (lane + 32 < F) p.lin[lane + 32][id1] = gl;
+        if (ok0) p.lin[lane][id0] = gl;
+        if (ok1) p.lin[lane + 32][id1] = gl;
       } else {
-        if (lane < F) { if (hints) red_add_f1_pol(p.lin[lane] + id0, gl, pol_keep); else red_add_f1(p.lin[lane] + id0, gl); }
-        if (lane + 32 < F) { if (hints) red_add_f1_pol(p.lin[lane + 32] + id1, gl, pol_keep); else red_add_f1(p.lin[lane + 32] + id1, gl); }
+        if (ok0) { if (hints) red_add_f1_pol(p.lin[lane] + id0, gl, pol_keep); else red_add_f1(p.lin[lane] + id0, gl); }
+        if (ok1) { if (hints) red_add_f1_pol(p.lin[lane + 32] + id1, gl, pol_keep); else red_add_f1(p.lin[lane + 32] + id1, gl); }
       }
     }
     id0 = nid0;
@@ -786,11 +802,13 @@ static b2ctr_status_t fill_uni(const b2ctr_uniform_gather_t* g, UniParams* p) {
     B2_REQUIRE(ft.idx && (g->world > 1 || (ft.table && aligned16(ft.table))),
                "uniform gather: feature %d bad pointers", f);
     p->table[f] = ft.table;
+    p->vocab[f] = ft.vocab;
     p->idx[f] = ft.idx;
     p->idx_stride[f] = ft.idx_stride;
     p->lin[f] = (g->lin_tables && g->world <= 1) ? g->lin_tables[f] : nullptr;
     B2_REQUIRE(g->world > 1 || !g->lin_tables || p->lin[f], "uniform gather: lin_tables[%d] is NULL", f);
   }
+  p->oob = oob_counter();
   p->xp_hi = p->xp_lo = nullptr;
   p->xp_pitch = 0;
   p->world = g->world > 1 ? g->world : 1;
@@ -840,6 +858,7 @@ b2ctr_status_t b2ctr_embed_gather_fwd(const b2ctr_feature_t* feats, int32_t nfea
   cudaStream_t st = (cudaStream_t)stream;
   for (int base = 0; base < nfeat; base += kFeatChunk) {
     FeatBlock fb;
+    fb.oob = oob_counter();
     fb.nfeat = nfeat - base < kFeatChunk ? nfeat - base : kFeatChunk;
     for (int i = 0; i < fb.nfeat; ++i) fb.f[i] = feats[base + i];
     B2_DISPATCH_G(embed_gather_generic_kernel, lanes, vec4, fb, batch);
@@ -858,6 +877,7 @@ b2ctr_status_t b2ctr_embed_scatter_add(const b2ctr_feature_t* feats, int32_t nfe
   cudaStream_t st = (cudaStream_t)stream;
   for (int base = 0; base < nfeat; base += kFeatChunk) {
     FeatBlock fb;
+    fb.oob = nullptr;            // the forward pass already counted them
     fb.nfeat = nfeat - base < kFeatChunk ? nfeat - base : kFeatChunk;
     for (int i = 0; i < fb.nfeat; ++i) fb.f[i] = feats[base + i];
     B2_DISPATCH_G(embed_scatter_generic_kernel, lanes, vec4, fb, batch, scale);

@@ -20,6 +20,8 @@ constexpr int kShardFeat = 64;
 struct ShardIdx {
   const void* idx[kShardFeat];
   int64_t stride[kShardFeat];
+  int64_t vocab[kShardFeat];     // FULL (unsharded) vocabulary of feature f
+  unsigned long long* oob;
   int32_t nfeat;
   int32_t dtype;
 };
@@ -51,7 +53,8 @@ __global__ void __launch_bounds__(256)
       if (item < total) {
         const int64_t b = item / si.nfeat;
         const int f = (int)(item - b * si.nfeat);
-        const int64_t id = load_idx(si.idx[f], b * si.stride[f], si.dtype);
+        int64_t id = load_idx(si.idx[f], b * si.stride[f], si.dtype);
+        if (!id_in_range(id, si.vocab[f])) { note_oob(si.oob); id = 0; }   // routed as row 0, raised by the host
         owner[u] = (int)(id % world);
         rank[u] = atomicAdd(&hist[owner[u]], 1);
       }
@@ -83,7 +86,8 @@ __global__ void __launch_bounds__(256)
        item += (int64_t)gridDim.x * blockDim.x) {
     const int64_t b = item / si.nfeat;
     const int f = (int)(item - b * si.nfeat);
-    const int64_t id = load_idx(si.idx[f], b * si.stride[f], si.dtype);
+    int64_t id = load_idx(si.idx[f], b * si.stride[f], si.dtype);
+    if (!id_in_range(id, si.vocab[f])) id = 0;
     const int64_t s = slot[item];
     const int owner = (int)(s >> 32);
     const int p = off[owner] + (int)(s & 0xffffffff);
@@ -157,11 +161,13 @@ __global__ void __launch_bounds__(256)
 static b2ctr_status_t fill_idx(const b2ctr_feature_t* feats, int32_t nfeat, ShardIdx* si) {
   B2_REQUIRE(feats && nfeat > 0 && nfeat <= kShardFeat, "shard: nfeat must be in [1,%d]", kShardFeat);
   si->nfeat = nfeat;
+  si->oob = oob_counter();
   si->dtype = feats[0].idx_dtype;
   for (int f = 0; f < nfeat; ++f) {
     B2_REQUIRE(feats[f].idx && feats[f].idx_dtype == si->dtype, "shard: feature %d bad idx / mixed dtypes", f);
     si->idx[f] = feats[f].idx;
     si->stride[f] = feats[f].idx_stride;
+    si->vocab[f] = feats[f].vocab;
   }
   return B2CTR_OK;
 }

@@ -127,11 +127,12 @@ def contiguous(var):
 
 
 class _TapeNode(object):
-    __slots__ = ("outputs", "backward")
+    __slots__ = ("outputs", "backward", "tag")
 
     def __init__(self, outputs, backward):
         self.outputs = outputs
         self.backward = backward
+        self.tag = K.PROFILE_TAG       # bench attribution: the backward launches join the forward's group
 
 
 class Tape(object):
@@ -151,7 +152,11 @@ class Tape(object):
                 grads = [o.grad for o in node.outputs]
                 if all(g is None for g in grads):
                     continue
-                node.backward(grads)
+                if node.tag is not None and K.PROFILE is not None:
+                    with K.profile_tag(node.tag):
+                        node.backward(grads)
+                else:
+                    node.backward(grads)
                 for o in node.outputs:
                     o.grad = None   # free as we go
         finally:
@@ -931,12 +936,27 @@ class Model(object):
                  **{w.name: w.value() for w in self.weights})
 
     def load_weights(self, path):
+        """By name; a checkpoint of an identically BUILT model whose automatic layer names differ (a second
+        model of the same process: ``dnn_1`` vs ``dnn``) is matched by topology order + shapes, like Keras' h5
+        loader does."""
         p = path if str(path).endswith(".npz") else str(path) + ".npz"
         data = np.load(p)
-        for w in self.weights:
-            if w.name not in data:
-                raise ValueError("weight %s missing from %s" % (w.name, p))
-            w.set_value(data[w.name])
+        ws = self.weights
+        if all(w.name in data for w in ws):
+            for w in ws:
+                w.set_value(data[w.name])
+            return
+        keys = list(data.files)                  # np.savez keeps insertion (= topology) order
+        if len(keys) != len(ws):
+            missing = [w.name for w in ws if w.name not in data]
+            raise ValueError("weight %s missing from %s (and %d stored arrays cannot be matched to %d weights by "
+                             "order)" % (missing[0], p, len(keys), len(ws)))
+        for w, k in zip(ws, keys):
+            if tuple(data[k].shape) != tuple(w.shape):
+                raise ValueError("weight %s missing from %s; by order it would take %s of shape %s, expected %s"
+                                 % (w.name, p, k, data[k].shape, w.shape))
+        for w, k in zip(ws, keys):
+            w.set_value(data[k])
 
     def count_params(self):
         return sum(w.numel() for w in self.weights)
@@ -956,6 +976,11 @@ class Model(object):
         (O(batch); l2 on tables must be 0), 'auto' = dense below 4M table elements."""
         self.optimizer = get_optimizer(optimizer)
         self.loss = loss
+        known = ("binary_crossentropy", "bce", "mse", "mean_squared_error", "logloss")
+        extra = [m for m in (metrics or []) if not (isinstance(m, str) and m in known)]
+        if extra:
+            import warnings
+            warnings.warn("metrics %r are not computed by this runtime (fit reports loss / val_loss only)" % (extra,))
         self.metrics = metrics or []
         self.metrics_names = ["loss"] + [m if isinstance(m, str) else m.__name__ for m in self.metrics]
         if embedding_update not in ("auto", "dense", "sparse"):
@@ -979,6 +1004,17 @@ class Model(object):
     def _materialize(self):
         for w in self.weights:
             w.materialize()
+
+    def _check_ids(self):
+        """Raise like TF-CPU's Embedding does (InvalidArgument: indices[...] is not in [0, V)) when a gather
+        kernel met an id outside its table since the last check.  The kernels themselves stay memory-safe:
+        such ids read a zero row and are never written (deepctr/inputs.py:101-130 relies on Keras for this).
+        Called where the host synchronises anyway (end of predict / evaluate / fit epoch, train_on_batch)."""
+        n = K.embed_oob_count(reset=True)
+        if n:
+            raise ValueError("%d embedding lookups used an id outside [0, vocabulary_size): check the "
+                             "vocabulary_size of the feature columns against the data (unseen categories at "
+                             "predict time, -1 for missing values...); the rows were read as zeros" % n)
 
     def close(self):
         """Release what must not outlive the process group: captured step graphs (they hold NCCL kernels) and
@@ -1189,11 +1225,15 @@ class Model(object):
 
     def train_on_batch(self, x, y, **kw):
         loss_sum, _, batch = self._loss_step(x, y, True)
-        return float(loss_sum.item()) / batch + self._reg_loss()
+        loss = float(loss_sum.item()) / batch + self._reg_loss()
+        self._check_ids()
+        return loss
 
     def test_on_batch(self, x, y, **kw):
         loss_sum, _, batch = self._loss_step(x, y, False)
-        return float(loss_sum.item()) / batch + self._reg_loss()
+        loss = float(loss_sum.item()) / batch + self._reg_loss()
+        self._check_ids()
+        return loss
 
     def _reg_loss(self):
         tot = 0.0
@@ -1215,6 +1255,8 @@ class Model(object):
         outs = []
         for s in range(0, n, batch_size):
             outs.append(self.predict_on_batch(slice_inputs(x, slice(s, min(n, s + batch_size)))).cpu())
+        if outs:
+            self._check_ids()
         return torch.cat(outs, 0).numpy() if outs else np.zeros((0, 1), np.float32)
 
     def evaluate(self, x, y, batch_size=32, verbose=0, **kw):
@@ -1226,11 +1268,16 @@ class Model(object):
             sl = slice(s, min(n, s + batch_size))
             ls, _, b = self._loss_step(slice_inputs(x, sl), y[sl], False)
             tot += float(ls.item())
+        if n:
+            self._check_ids()
         return tot / max(n, 1) + self._reg_loss()
 
     def fit(self, x=None, y=None, batch_size=32, epochs=1, verbose=1, validation_split=0.0,
             validation_data=None, shuffle=True, callbacks=None, **kw):
         from .inputs import slice_inputs
+        if callbacks:
+            import warnings
+            warnings.warn("fit(callbacks=...) is not supported by this runtime: %d callback(s) ignored" % len(callbacks))
         n = self._num_samples(x)
         y = np.asarray(y)
         hist = History()
@@ -1316,7 +1363,8 @@ class Model(object):
                 permits.release()
                 worker.join()
                 sys.setswitchinterval(switch0)
-            self.d2h_bytes = getattr(self, "d2h_bytes", 0) + 4 * nsteps
+            self.d2h_bytes = getattr(self, "d2h_bytes", 0) + 4 * nsteps + 8
+            self._check_ids()
             tot = float(host_losses[:nsteps].double().sum()) if nsteps else 0.0
             logs = {"loss": tot / max(cnt, 1) + self._reg_loss()}
             if val is not None:

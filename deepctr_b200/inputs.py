@@ -369,12 +369,27 @@ class EmbeddingPlanner(object):
         if sparse and optimizer.name != "sgd":
             raise ValueError("embedding_update='sparse' (tables too large for dense updates) supports the "
                              "'sgd' optimizer only; got %r" % optimizer.name)
-        for w in self.tables():
+        tabs = list(self.tables())
+        for l in self.model.layers:          # unplanned Embedding layers follow the same policy
+            if isinstance(l, Embedding) and all(l.embeddings is not w for w in tabs):
+                tabs.append(l.embeddings)
+        if sparse:
+            # the fused row-wise update touches only the rows of the batch: a whole-table L2 penalty (the
+            # builders' default l2_reg_embedding / l2_reg_linear = 1e-5, Keras semantics: SURVEY.md App. C)
+            # cannot be part of it.  Never drop it silently.
+            reg = sorted(w.name for w in tabs if w.trainable and w.l2 > 0)
+            if reg and mode == "sparse":
+                raise ValueError("embedding_update='sparse' applies row-wise updates and cannot apply the L2 "
+                                 "regulariser of %s ... (%d tables): build the model with l2_reg_embedding=0 and "
+                                 "l2_reg_linear=0, or use embedding_update='dense'" % (reg[0], len(reg)))
+            if reg:
+                import warnings
+                warnings.warn("tables of %d elements take the row-wise (sparse) update path, which does NOT apply "
+                              "the L2 regulariser of %s ... (%d tables); pass l2_reg_embedding=0 / l2_reg_linear=0 "
+                              "to silence this, or embedding_update='dense' for Keras' O(vocabulary) semantics"
+                              % (total, reg[0], len(reg)))
+        for w in tabs:
             w.sparse_grad = bool(sparse and w.trainable)
-        # unplanned Embedding layers follow the same policy
-        for l in self.model.layers:
-            if isinstance(l, Embedding):
-                l.embeddings.sparse_grad = bool(sparse and l.embeddings.trainable)
 
     def set_dist(self, ctx):
         """Row-shard the fast-path tables (and their dim-1 linear twins) over the process group:
@@ -383,11 +398,22 @@ class EmbeddingPlanner(object):
         self.dist = ctx
         self.exchange = parallel.ShardedExchange(ctx, K)
         self.sharded = False
-        if not self.fast or ctx.world == 1:
+        if ctx.world == 1:
             return
-        lin_ok = self._lin_matches_fast()
-        if self.lin and not lin_ok:
-            return        # unusual graph: keep the tables replicated (dense gradients are all-reduced)
+        lin_ok = self.fast and self._lin_matches_fast()
+        shardable = self.fast and (lin_ok or not self.lin)
+        will_shard = set()
+        if shardable:
+            for s_ in list(self.main[:self.fast_n]) + (list(self.lin) if lin_ok else []):
+                will_shard.add(id(s_.emb.embeddings))
+        # Every table that stays REPLICATED must take the dense path: its gradient is then part of the bucket
+        # all-reduced over the ranks.  A row-wise local update from this rank's mini-batch alone would let the
+        # replicas drift apart.
+        for l in self.model.layers:
+            if isinstance(l, Embedding) and id(l.embeddings) not in will_shard:
+                l.embeddings.sparse_grad = False
+        if not shardable:
+            return        # unusual graph: every table replicated, gradients all-reduced like the dense weights
         if self.optimizer is None or self.optimizer.name != "sgd":
             raise ValueError("row-sharded embeddings need the 'sgd' optimizer (fused row-wise update)")
         seen = set()
@@ -591,10 +617,11 @@ class EmbeddingPlanner(object):
         if length is not None and length.dtype != torch.int32:
             raise ValueError("sequence lengths must be int32")
         tab = table if table is not None else s.emb.embeddings.materialize()
+        shard = s.emb.embeddings.opt_state.get("shard")        # (rank, world, full vocabulary) when row-sharded
         return K.make_feature(tab, ids, out, out_col=s.col if s.buf != "seq" else 0, out_ld=out_ld,
                               maxlen=s.maxlen, pool=s.pool, mask_mode=s.mask_mode, length=length,
                               weight=weight, weight_mode=s.weight_mode, hash_mode=s.hash[0],
-                              src_table=src_table)
+                              src_table=src_table, vocab=shard[2] if shard else s.emb.input_dim)
 
     @staticmethod
     def _target(w, opt):

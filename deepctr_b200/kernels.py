@@ -56,8 +56,9 @@ def idx_dtype(t):
 # ---- embedding ------------------------------------------------------------------------------
 def make_feature(table, idx, out, out_col=0, out_ld=None, maxlen=1, pool=L.POOL_NONE,
                  mask_mode=L.MASK_NONE, length=None, weight=None, weight_mode=L.WEIGHT_NONE,
-                 hash_mode=L.HASH_NONE, idx_stride=None, src_table=None):
-    """Fill one b2ctr_feature_t.  ``idx`` is [B] / [B,1] / [B,T] (or a strided column view)."""
+                 hash_mode=L.HASH_NONE, idx_stride=None, src_table=None, vocab=None):
+    """Fill one b2ctr_feature_t.  ``idx`` is [B] / [B,1] / [B,T] (or a strided column view).  ``vocab``:
+    the FULL vocabulary when ``table`` is only a shard of it (ids are validated against it)."""
     _require_cuda(table, idx, out)
     f = L.Feature()
     f.table = table.data_ptr()
@@ -68,7 +69,7 @@ def make_feature(table, idx, out, out_col=0, out_ld=None, maxlen=1, pool=L.POOL_
     f.len_stride = length.stride(0) if (length is not None and length.dim() >= 1 and length.shape[0] > 1) else 0
     f.weight_ld = weight.stride(0) if (weight is not None and weight.dim() >= 2 and weight.shape[0] > 1) else 0
     f.out = out.data_ptr()
-    f.vocab = table.shape[0]
+    f.vocab = table.shape[0] if vocab is None else int(vocab)
     f.dim = table.shape[1] if table.dim() > 1 else 1
     f.idx_stride = idx_stride if idx_stride is not None else (idx.stride(0) if idx.dim() >= 1 else 1)
     f.out_ld = out_ld if out_ld is not None else out.stride(0)
@@ -91,6 +92,14 @@ def _feat_array(feats):
 def embed_gather_fwd(feats, batch):
     arr = _feat_array(feats)
     L.check(L.lib().b2ctr_embed_gather_fwd(arr, len(feats), batch, stream()), "embed_gather_fwd")
+
+
+def embed_oob_count(reset=True):
+    """Number of embedding ids outside [0, vocabulary_size) the gather kernels of this device have seen
+    (they read a zero row and are skipped by the updates).  Synchronises the current stream."""
+    n = C.c_int64(0)
+    L.check(L.lib().b2ctr_embed_oob_count(C.byref(n), 1 if reset else 0, stream()), "embed_oob_count")
+    return int(n.value)
 
 
 def embed_scatter_add(feats, batch, scale):
@@ -383,6 +392,22 @@ def adagrad_step(w, g, acc, lr, eps=1e-7, l2=0.0):
 
 # ---- optional per-kernel timing (bench.py): CUDA events around each launch on the launching stream --
 PROFILE = None
+PROFILE_TAG = None       # set by `profile_tag(...)`: the launch is recorded as "<tag>:<wrapper name>"
+
+
+class profile_tag(object):
+    """Attribute the launches of a region (CIN layers, the DIN attention unit ...) to a named group."""
+
+    def __init__(self, tag):
+        self.tag = tag
+
+    def __enter__(self):
+        global PROFILE_TAG
+        self.prev, PROFILE_TAG = PROFILE_TAG, (self.tag if PROFILE_TAG is None else PROFILE_TAG)
+
+    def __exit__(self, *a):
+        global PROFILE_TAG
+        PROFILE_TAG = self.prev
 
 
 def _timed(fn):
@@ -396,7 +421,7 @@ def _timed(fn):
         e0.record()
         r = fn(*a, **k)
         e1.record()
-        prof.setdefault(name, []).append((e0, e1))
+        prof.setdefault(name if PROFILE_TAG is None else "%s:%s" % (PROFILE_TAG, name), []).append((e0, e1))
         return r
 
     wrap.__name__ = name
@@ -643,4 +668,11 @@ def shard_scatter_rows(tables, lin_tables, dim, keys, n, grows, glin, scale, lin
 
 
 for _n in ("shard_bucketize", "shard_fill", "shard_gather_rows", "shard_scatter_rows"):
+    globals()[_n] = _timed(globals()[_n])
+
+
+for _n in ("ewise", "cross_vector_fwd", "cross_vector_bwd", "cin_outer_fwd", "cin_outer_bwd", "cin_sum_d",
+           "cin_expand_grad", "interacting_fwd", "interacting_bwd", "din_att_input_fwd", "din_att_input_bwd",
+           "din_pool_fwd", "din_pool_bwd", "seqpool_fwd", "seqpool_bwd", "seqweight", "seqscale", "colstats",
+           "moving_update", "bn_apply", "bn_bwd", "dice_fwd", "dice_bwd", "dropout"):
     globals()[_n] = _timed(globals()[_n])

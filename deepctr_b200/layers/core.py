@@ -108,8 +108,7 @@ class PredictionLayer(Layer):
 
     def call(self, inputs, **kwargs):
         from .. import kernels as K
-        if self.task == "multiclass":
-            raise NotImplementedError("multiclass PredictionLayer is outside the hot path")
+        # "multiclass" is, in the reference, exactly "no sigmoid" (core.py:250-257): bias, then reshape(-1, 1)
         lt = E.contiguous(inputs).reshape(-1)
         bias = self.global_bias.materialize() if self.use_bias else None
         task = L.TASK_BINARY if self.task == "binary" else L.TASK_REGRESSION

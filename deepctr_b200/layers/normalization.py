@@ -1,5 +1,5 @@
 """BatchNormalization / Dropout used by DNN(use_bn, dropout_rate) (deepctr/layers/core.py:177-179) and
-LayerNormalization (deepctr/layers/normalization.py:18-51, Transformer-only: out of the hot path)."""
+(The reference's LayerNormalization, deepctr/layers/normalization.py:18-51, is Transformer-only: out of scope.)"""
 from .. import ops
 from ..engine import Layer, Zeros, Ones
 
@@ -35,9 +35,3 @@ class Dropout(Layer):
             return inputs
         self._calls += 1
         return ops.dropout(inputs, self.rate, (self.seed or 0) * 1000003 + self._calls)
-
-
-class LayerNormalization(Layer):
-    def __init__(self, axis=-1, eps=1e-9, center=True, scale=True, **kwargs):
-        Layer.__init__(self, **kwargs)
-        raise NotImplementedError("LayerNormalization is only used by Transformer/BST/DSIN (SURVEY.md 2 #3f)")

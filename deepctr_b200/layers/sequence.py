@@ -10,14 +10,6 @@ from ..engine import Layer
 from .core import LocalActivationUnit
 
 
-def _mask_of(mask):
-    if mask is None:
-        return None
-    if isinstance(mask, list):
-        return mask
-    return mask
-
-
 class SequencePoolingLayer(Layer):
     """sum / mean / max over the valid positions of [B,T,E] -> [B,1,E]."""
 
@@ -140,8 +132,10 @@ class AttentionSequencePoolingLayer(Layer):
         else:
             queries, keys, keys_length = inputs
             key_mask = E.KMask(lengths=keys_length.data.reshape(-1), maxlen=keys.data.shape[1]).materialize()
-        score = self.local_att.call([queries, keys], training=training)      # [B,T,1]
-        return ops.din_attention_pool(score, keys, key_mask, self.weight_normalization, self.return_score)
+        from .. import kernels as K
+        with K.profile_tag("din_att"):
+            score = self.local_att.call([queries, keys], training=training)      # [B,T,1]
+            return ops.din_attention_pool(score, keys, key_mask, self.weight_normalization, self.return_score)
 
     def compute_output_shape(self, input_shape):
         if self.return_score:

@@ -230,6 +230,8 @@ def concat(xs, axis=-1):
                 return _window(base, xs[0].col0, col - xs[0].col0, tuple(out_shape))
     if any(v.data is None for v in xs):
         raise L.B2ctrError("a fused-away (virtual) embedding output reached a layer that needs its values")
+    if flat_ok:
+        # per-sample flat concatenation of non-adjacent windows: strided 2-D copies, no densifying pass
         out = _empty((b, sum(widths)), xs[0].data)
         col = 0
         for v, w in zip(xs, widths):
@@ -492,6 +494,11 @@ CIN_CHUNK_BYTES = 48 << 20      # outer-product chunk kept well inside the 126 M
 
 
 def cin(x, filters, biases, layer_size, activation, split_half):
+    with K.profile_tag("cin"):
+        return _cin(x, filters, biases, layer_size, activation, split_half)
+
+
+def _cin(x, filters, biases, layer_size, activation, split_half):
     """Compressed Interaction Network (layers/interaction.py:277-325).  Per batch chunk the outer
     product Z[(b,d), i*H+j] lives in an L2-sized scratch buffer and is contracted with the filter by
     b2ctr_gemm; layer outputs are kept as [B, D, N] so the next layer reads them through strides."""
@@ -538,6 +545,10 @@ def cin(x, filters, biases, layer_size, activation, split_half):
     res = E.Var(out)
 
     def bwd(grads):
+        with K.profile_tag("cin"):
+            _bwd(grads)
+
+    def _bwd(grads):
         g = grads[0]
         if not g.is_contiguous():
             g = g.contiguous()

@@ -176,6 +176,14 @@ B2CTR_API b2ctr_status_t b2ctr_embed_scatter_uniform_bwd(const b2ctr_uniform_gat
                                                         float lin_scale, int64_t batch,
                                                         void* stream);
 
+/* Ids outside [0, vocab) (b2ctr_feature_t.vocab = the FULL vocabulary_size, also for row-sharded tables):
+ * every gather kernel returns a ZERO row for them and every update kernel skips them - no out-of-bounds
+ * access in either direction (tf.keras.layers.Embedding on a GPU returns zeros, on a CPU it raises
+ * InvalidArgument; deepctr/inputs.py:101-130 just calls it).  The kernels count such ids in a per-device
+ * counter; this call reads (and optionally resets) it, synchronising `stream` - the host mirror raises
+ * ValueError like TF-CPU when it is non-zero. */
+B2CTR_API b2ctr_status_t b2ctr_embed_oob_count(int64_t* count, int32_t reset, void* stream);
+
 /* Hash (deepctr/layers/utils.py:89-112): ids -> int64 buckets, FarmHash Fingerprint64 of the
  * decimal ASCII form.  mask_zero: 0 stays 0, others land in [1, num_buckets).               */
 B2CTR_API b2ctr_status_t b2ctr_hash64(const void* ids, int32_t idx_dtype, int64_t n,

@@ -273,3 +273,104 @@ def test_uniform_gather_emits_operand_planes(cuda):
     plan2.g.x_planes_cols = kd
     with pytest.raises(ValueError):
         K.embed_gather_uniform_fwd(plan2, 300)
+
+
+# ---- ids outside [0, vocab): zero rows, no out-of-bounds access in either direction, counted ----------
+def test_out_of_range_ids_generic(cuda):
+    K, L = _kern()
+    rng = np.random.RandomState(11)
+    B, T, V, dim = 64, 5, 37, 8
+    host, dev = _mk_tables(rng, 1, V, dim, cuda, std=1.0)
+    K.embed_oob_count(reset=True)
+    idx = rng.randint(0, V, size=(B, T))
+    idx[3, 1], idx[7, 0], idx[9, 4] = -1, V, 10 ** 9
+    bad = (idx < 0) | (idx >= V)
+    idx_t = torch.tensor(idx, dtype=torch.int32)
+    out = torch.full((B, T * dim), 5.0, device=cuda)
+    K.embed_gather_fwd([K.make_feature(dev[0], idx_t.to(cuda), out, maxlen=T)], B)
+    want = host[0][torch.tensor(np.where(bad, 0, idx))].clone()
+    want[torch.tensor(bad)] = 0.0
+    assert torch.equal(out.cpu().reshape(B, T, dim), want)
+    assert K.embed_oob_count(reset=True) == int(bad.sum())
+    assert K.embed_oob_count(reset=True) == 0
+    # pooled sum: an out-of-range id contributes a zero row
+    pooled = torch.empty((B, dim), device=cuda)
+    K.embed_gather_fwd([K.make_feature(dev[0], idx_t.to(cuda), pooled, maxlen=T, pool=L.POOL_SUM)], B)
+    acc = torch.zeros(B, dim)
+    for t in range(T):
+        acc = acc + want[:, t, :]
+    assert torch.equal(pooled.cpu(), acc)
+    assert K.embed_oob_count(reset=True) == int(bad.sum())
+    # scatter: guard rows around the table stay untouched, valid rows are updated
+    guard = torch.zeros((V + 2, dim), device=cuda)
+    tab = guard[1:V + 1]
+    g = torch.ones((B, T * dim), device=cuda)
+    K.embed_scatter_add([K.make_feature(tab, idx_t.to(cuda), g, maxlen=T)], B, 1.0)
+    gh = guard.cpu()
+    assert torch.all(gh[0] == 0) and torch.all(gh[V + 1] == 0)
+    counts = np.bincount(idx[~bad].reshape(-1), minlength=V).astype(np.float32)
+    assert torch.equal(gh[1:V + 1, 0], torch.tensor(counts))
+
+
+@pytest.mark.parametrize("dim", [8, 32])
+def test_out_of_range_ids_uniform(cuda, dim):
+    K, L = _kern()
+    rng = np.random.RandomState(12)
+    B, F, V = 96, 6, 41
+    host, dev = _mk_tables(rng, F, V, dim, cuda, std=0.5)
+    lin_d = [torch.tensor(rng.normal(size=(V,)).astype(np.float32)).to(cuda) for _ in range(F)]
+    idx = rng.randint(0, V, size=(B, F))
+    idx[0, 0], idx[5, 3], idx[95, 5] = -7, V, V + 100
+    bad = (idx < 0) | (idx >= V)
+    idx_d = torch.tensor(idx, dtype=torch.int32).to(cuda)
+    ldx = F * dim
+    x = torch.full((B, ldx), 3.0, device=cuda)
+    linear = torch.empty((B,), device=cuda)
+    fm = torch.empty((B,), device=cuda)
+    feats = [K.make_feature(dev[f], idx_d[:, f], x) for f in range(F)]
+    plan = K.UniformPlan(feats, lin_d, None, x, linear, fm, (1 << F) - 1)
+    K.embed_oob_count(reset=True)
+    K.embed_gather_uniform_fwd(plan, B)
+    got = x.cpu().reshape(B, F, dim)
+    safe = np.where(bad, 0, idx)
+    for f in range(F):
+        want = host[f][torch.tensor(safe[:, f])].clone()
+        want[torch.tensor(bad[:, f])] = 0.0
+        assert torch.equal(got[:, f, :], want)
+    lin_want = sum(torch.where(torch.tensor(bad[:, f]), torch.zeros(B), lin_d[f].cpu()[torch.tensor(safe[:, f])])
+                   for f in range(F))
+    torch.testing.assert_close(linear.cpu(), lin_want, rtol=1e-5, atol=1e-5)
+    assert K.embed_oob_count(reset=True) == int(bad.sum())
+    # backward into guarded copies of the tables
+    guards = [torch.zeros((V + 2, dim), device=cuda) for _ in range(F)]
+    lguards = [torch.zeros((V + 2,), device=cuda) for _ in range(F)]
+    feats_b = [K.make_feature(guards[f][1:V + 1], idx_d[:, f], x) for f in range(F)]
+    bplan = K.UniformPlan(feats_b, [lg[1:V + 1] for lg in lguards], None, x, None, None, (1 << F) - 1)
+    dx = torch.ones((B, ldx), device=cuda)
+    dlin = torch.ones((B,), device=cuda)
+    K.embed_scatter_uniform_bwd(bplan, dx, None, dlin, 1.0, 1.0, B)
+    for f in range(F):
+        gh, lh = guards[f].cpu(), lguards[f].cpu()
+        assert torch.all(gh[0] == 0) and torch.all(gh[V + 1] == 0) and lh[0] == 0 and lh[V + 1] == 0
+        counts = np.bincount(idx[~bad[:, f], f], minlength=V).astype(np.float32)
+        assert torch.equal(gh[1:V + 1, 0], torch.tensor(counts))
+        assert torch.equal(lh[1:V + 1], torch.tensor(counts))
+
+
+def test_model_raises_on_out_of_range_ids(cuda):
+    """host mirror of TF-CPU's InvalidArgument: predict / train_on_batch raise ValueError."""
+    import b2_helpers as H
+    from deepctr_b200.models import DeepFM
+    rng = np.random.RandomState(13)
+    cols, x, y = H.criteo_like(rng, 64)
+    model = DeepFM(cols, cols, dnn_hidden_units=(8,))
+    model.compile("sgd", "binary_crossentropy")
+    assert model.predict(x, batch_size=64).shape == (64, 1)
+    x["C0"] = x["C0"].copy()
+    x["C0"][5] = -1
+    with pytest.raises(ValueError, match="outside"):
+        model.predict(x, batch_size=64)
+    with pytest.raises(ValueError, match="outside"):
+        model.train_on_batch(x, y)
+    x["C0"][5] = 0
+    model.train_on_batch(x, y)          # the counter was reset: clean data passes again

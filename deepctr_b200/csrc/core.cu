@@ -63,6 +63,25 @@ b2ctr_status_t b2ctr_set_l2_fetch_granularity(int32_t bytes) {
   }
   return B2CTR_OK;
 }
+b2ctr_status_t b2ctr_l2_persist_reserve(int64_t bytes, int64_t* granted, int64_t* max_window) {
+  int dev = 0, max_persist = 0, max_win = 0;
+  cudaError_t e = cudaGetDevice(&dev);
+  if (e == cudaSuccess) e = cudaDeviceGetAttribute(&max_persist, cudaDevAttrMaxPersistingL2CacheSize, dev);
+  if (e == cudaSuccess) e = cudaDeviceGetAttribute(&max_win, cudaDevAttrMaxAccessPolicyWindowSize, dev);
+  size_t want = bytes < 0 ? 0 : (size_t)bytes;
+  if (want > (size_t)max_persist) want = (size_t)max_persist;
+  if (e == cudaSuccess) e = cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, want);
+  size_t got = 0;
+  if (e == cudaSuccess) e = cudaDeviceGetLimit(&got, cudaLimitPersistingL2CacheSize);
+  if (e != cudaSuccess) {
+    b2ctr::set_error("l2_persist_reserve(%lld): %s", (long long)bytes, cudaGetErrorString(e));
+    cudaGetLastError();
+    return B2CTR_ERR_CUDA;
+  }
+  if (granted) *granted = (int64_t)got;
+  if (max_window) *max_window = (int64_t)max_win;
+  return B2CTR_OK;
+}
 b2ctr_status_t b2ctr_enable_peer_access(int32_t peer_device) {
   cudaError_t e = cudaDeviceEnablePeerAccess(peer_device, 0);
   if (e == cudaErrorPeerAccessAlreadyEnabled) {

@@ -783,6 +783,31 @@ static b2ctr_status_t validate_feats(const b2ctr_feature_t* feats, int32_t nfeat
     }                                                                                    \
   } while (0)
 
+// <<<grid, 256, 0, st>>> with an optional persisting-L2 access-policy window as a launch attribute (it
+// becomes a kernel-node attribute when the step is captured into a CUDA graph)
+template <typename... KArgs, typename... Args>
+static cudaError_t launch_uni(void (*kern)(KArgs...), int grid, cudaStream_t st, const b2ctr_uniform_gather_t* g,
+                              Args... args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3((unsigned)grid);
+  cfg.blockDim = dim3(256);
+  cfg.dynamicSmemBytes = 0;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  cfg.attrs = attr;
+  cfg.numAttrs = 0;
+  if (g->l2_window && g->l2_window_bytes > 0) {
+    attr[0].id = cudaLaunchAttributeAccessPolicyWindow;
+    attr[0].val.accessPolicyWindow.base_ptr = const_cast<void*>(g->l2_window);
+    attr[0].val.accessPolicyWindow.num_bytes = (size_t)g->l2_window_bytes;
+    attr[0].val.accessPolicyWindow.hitRatio = g->l2_hit_ratio > 0.f ? (g->l2_hit_ratio < 1.f ? g->l2_hit_ratio : 1.f) : 1.f;
+    attr[0].val.accessPolicyWindow.hitProp = cudaAccessPropertyPersisting;
+    attr[0].val.accessPolicyWindow.missProp = cudaAccessPropertyStreaming;
+    cfg.numAttrs = 1;
+  }
+  return cudaLaunchKernelEx(&cfg, kern, args...);
+}
+
 static b2ctr_status_t fill_uni(const b2ctr_uniform_gather_t* g, UniParams* p) {
   B2_REQUIRE(g && g->feats && g->x, "uniform gather: NULL descriptor / feats / x");
   B2_REQUIRE(g->nfeat > 0 && g->nfeat <= kUniMaxFeat, "uniform gather: nfeat must be in [1,%d]",
@@ -837,7 +862,7 @@ static b2ctr_status_t fill_uni(const b2ctr_uniform_gather_t* g, UniParams* p) {
   p->has_lin = g->world > 1 ? (g->peer_lin_tables != nullptr) : (g->lin_tables != nullptr);
   static int hints = -1;
   if (hints < 0) { const char* ev = getenv("B2CTR_L2_HINTS"); hints = ev ? atoi(ev) : 1; }
-  p->l2_hints = hints;
+  p->l2_hints = (g->l2_window && g->l2_window_bytes > 0) ? 0 : hints;   // the window replaces the per-load hints
   p->store_grads = (g->flags & B2CTR_UNIFORM_STORE_GRADS) ? 1 : 0;
   return B2CTR_OK;
 }
@@ -888,12 +913,12 @@ b2ctr_status_t b2ctr_embed_scatter_add(const b2ctr_feature_t* feats, int32_t nfe
 
 #define B2_DISPATCH_LPR1(KERNEL, SH, dim, ...)                                 \
   switch ((dim) / 4) {                                                         \
-    case 1: KERNEL<1, SH><<<grid, 256, 0, st>>>(__VA_ARGS__); break;           \
-    case 2: KERNEL<2, SH><<<grid, 256, 0, st>>>(__VA_ARGS__); break;           \
-    case 4: KERNEL<4, SH><<<grid, 256, 0, st>>>(__VA_ARGS__); break;           \
-    case 8: KERNEL<8, SH><<<grid, 256, 0, st>>>(__VA_ARGS__); break;           \
-    case 16: KERNEL<16, SH><<<grid, 256, 0, st>>>(__VA_ARGS__); break;         \
-    default: KERNEL<32, SH><<<grid, 256, 0, st>>>(__VA_ARGS__); break;         \
+    case 1: le = launch_uni(KERNEL<1, SH>, grid, st, g, __VA_ARGS__); break;   \
+    case 2: le = launch_uni(KERNEL<2, SH>, grid, st, g, __VA_ARGS__); break;   \
+    case 4: le = launch_uni(KERNEL<4, SH>, grid, st, g, __VA_ARGS__); break;   \
+    case 8: le = launch_uni(KERNEL<8, SH>, grid, st, g, __VA_ARGS__); break;   \
+    case 16: le = launch_uni(KERNEL<16, SH>, grid, st, g, __VA_ARGS__); break; \
+    default: le = launch_uni(KERNEL<32, SH>, grid, st, g, __VA_ARGS__); break; \
   }
 #define B2_DISPATCH_LPR(KERNEL, dim, ...)                                      \
   if (p.world > 1) { B2_DISPATCH_LPR1(KERNEL, true, dim, __VA_ARGS__) }        \
@@ -920,25 +945,31 @@ b2ctr_status_t b2ctr_embed_gather_uniform_fwd(const b2ctr_uniform_gather_t* g, i
 #define B2_GATHER_CASE(LPRV)                                                                         \
   case LPRV:                                                                                         \
     if (p.world > 1) {                                                                               \
-      if (p.xp_hi) gather_uniform_fwd_kernel<LPRV, true, true><<<grid, 256, 0, st>>>(p, batch);      \
-      else gather_uniform_fwd_kernel<LPRV, true, false><<<grid, 256, 0, st>>>(p, batch);             \
+      if (p.xp_hi) le = launch_uni(gather_uniform_fwd_kernel<LPRV, true, true>, grid, st, g, p, batch);      \
+      else le = launch_uni(gather_uniform_fwd_kernel<LPRV, true, false>, grid, st, g, p, batch);             \
     } else {                                                                                         \
-      if (p.xp_hi) gather_uniform_fwd_kernel<LPRV, false, true><<<grid, 256, 0, st>>>(p, batch);     \
-      else gather_uniform_fwd_kernel<LPRV, false, false><<<grid, 256, 0, st>>>(p, batch);            \
+      if (p.xp_hi) le = launch_uni(gather_uniform_fwd_kernel<LPRV, false, true>, grid, st, g, p, batch);     \
+      else le = launch_uni(gather_uniform_fwd_kernel<LPRV, false, false>, grid, st, g, p, batch);            \
     }                                                                                                \
     break;
+  cudaError_t le = cudaSuccess;
   switch (p.dim / 4) {
     B2_GATHER_CASE(1) B2_GATHER_CASE(2) B2_GATHER_CASE(4) B2_GATHER_CASE(8) B2_GATHER_CASE(16)
     default:
       if (p.world > 1) {
-        if (p.xp_hi) gather_uniform_fwd_kernel<32, true, true><<<grid, 256, 0, st>>>(p, batch);
-        else gather_uniform_fwd_kernel<32, true, false><<<grid, 256, 0, st>>>(p, batch);
+        if (p.xp_hi) le = launch_uni(gather_uniform_fwd_kernel<32, true, true>, grid, st, g, p, batch);
+        else le = launch_uni(gather_uniform_fwd_kernel<32, true, false>, grid, st, g, p, batch);
       } else {
-        if (p.xp_hi) gather_uniform_fwd_kernel<32, false, true><<<grid, 256, 0, st>>>(p, batch);
-        else gather_uniform_fwd_kernel<32, false, false><<<grid, 256, 0, st>>>(p, batch);
+        if (p.xp_hi) le = launch_uni(gather_uniform_fwd_kernel<32, false, true>, grid, st, g, p, batch);
+        else le = launch_uni(gather_uniform_fwd_kernel<32, false, false>, grid, st, g, p, batch);
       }
   }
 #undef B2_GATHER_CASE
+  if (le != cudaSuccess) {
+    set_error("b2ctr_embed_gather_uniform_fwd: launch failed: %s", cudaGetErrorString(le));
+    cudaGetLastError();
+    return B2CTR_ERR_CUDA;
+  }
   B2_CHECK_LAUNCH("b2ctr_embed_gather_uniform_fwd");
   return B2CTR_OK;
 }
@@ -953,7 +984,13 @@ b2ctr_status_t b2ctr_embed_scatter_uniform_bwd(const b2ctr_uniform_gather_t* g, 
   if (batch <= 0) return B2CTR_OK;
   cudaStream_t st = (cudaStream_t)stream;
   const int grid = grid_for(batch, 8, 8);
+  cudaError_t le = cudaSuccess;
   B2_DISPATCH_LPR(scatter_uniform_bwd_kernel, p.dim, p, dx, dfm, dlinear, scale, lin_scale, batch);
+  if (le != cudaSuccess) {
+    set_error("b2ctr_embed_scatter_uniform_bwd: launch failed: %s", cudaGetErrorString(le));
+    cudaGetLastError();
+    return B2CTR_ERR_CUDA;
+  }
   B2_CHECK_LAUNCH("b2ctr_embed_scatter_uniform_bwd");
   return B2CTR_OK;
 }

@@ -17,6 +17,7 @@
 //   warp 8     : one elected lane issues tcgen05.mma (SS form, cta_group::1, M=128, N=BN, K=16) x 4 K-steps
 //                x 3 split terms per stage, then tcgen05.commit to release the stage / publish the tile.
 // Stages: kStages x (A hi+lo 32 KB + B hi+lo BN*256 B).  TMEM: BN fp32 columns x 128 lanes.
+#include <cuda.h>          // CUtensorMap + enums only: the encoder is resolved through the runtime (no libcuda link)
 #include <cuda_bf16.h>
 #include <stdlib.h>
 #include "common.cuh"
@@ -737,8 +738,28 @@ __device__ __forceinline__ void umma_commit_ws(uint64_t* bar) {
   }
 }
 
-template <int BN, int STAGES, int NCTA>
-__global__ void __launch_bounds__(kWsThreads, 1) gemm_planes_ws_kernel(const __grid_constant__ WsArgs w) {
+// ---- TMA (cp.async.bulk.tensor) producer primitives --------------------------------------------------
+// One elected thread arms the stage's mbarrier with the bytes that will land (expect_tx) and issues the
+// tiled bulk copies; the hardware writes the 128-byte-swizzled rows itself (CU_TENSOR_MAP_SWIZZLE_128B is
+// exactly the `chunk ^ (row & 7)` layout the UMMA descriptors above expect) and completes the barrier.
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map, int32_t c0, int32_t c1, uint64_t* bar) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];" ::"r"(dst),
+      "l"(map), "r"(c0), "r"(c1), "r"(smem_u32(bar))
+      : "memory");
+}
+__device__ __forceinline__ void tma_prefetch_desc(const CUtensorMap* map) {
+  asm volatile("prefetch.tensormap [%0];" ::"l"(map) : "memory");
+}
+
+template <int BN, int STAGES, int NCTA, bool TMA>
+__global__ void __launch_bounds__(kWsThreads, 1)
+    gemm_planes_ws_kernel(const __grid_constant__ WsArgs w, const __grid_constant__ CUtensorMap tm_ah,
+                          const __grid_constant__ CUtensorMap tm_al, const __grid_constant__ CUtensorMap tm_bh,
+                          const __grid_constant__ CUtensorMap tm_bl) {
   const PlaneArgs& g = w.p;
   constexpr int BNH = BN / NCTA;             // rows of the B tile staged by one CTA
   constexpr int A_PLANE = kTM * 128;
@@ -757,7 +778,8 @@ __global__ void __launch_bounds__(kWsThreads, 1) gemm_planes_ws_kernel(const __g
 
   if (threadIdx.x == 0) {
     for (int s = 0; s < STAGES; ++s) {
-      mbar_init(&full_bar[s], kWsProducers * 32);     // one deferred arrival per producer thread of THIS CTA
+      // cp.async producers: one deferred arrival per producer thread of THIS CTA; TMA: one arrive.expect_tx
+      mbar_init(&full_bar[s], TMA ? 1 : kWsProducers * 32);
       mbar_init(&peer_full[s], 1);                    // leader only: the peer CTA's half of the stage landed
       mbar_init(&empty_bar[s], 1);
     }
@@ -798,7 +820,51 @@ __global__ void __launch_bounds__(kWsThreads, 1) gemm_planes_ws_kernel(const __g
   };
 
   constexpr int kMmaWarp = kWsEpilogueWarps + kWsProducers;
-  if (warp >= kWsEpilogueWarps && warp < kMmaWarp) {
+  if (TMA && warp >= kWsEpilogueWarps && warp < kMmaWarp) {
+    // ------------------------------------------------------------------------------ TMA producer
+    // warp 8, one elected lane: wait for a free stage, arm its barrier with the stage bytes, issue the bulk
+    // tensor copies of the four operand planes.  No registers, no per-element instructions, no proxy fence:
+    // data moves global -> swizzled shared memory inside the async proxy, where tcgen05.mma reads it.
+    if (warp == kWsEpilogueWarps && lane == 0) {
+      tma_prefetch_desc(&tm_ah); tma_prefetch_desc(&tm_al); tma_prefetch_desc(&tm_bh); tma_prefetch_desc(&tm_bl);
+      uint32_t it = 0;
+      for (int64_t tile = cluster_id; tile < w.ntiles; tile += nclusters) {
+        int64_t mt, nt, kbeg;
+        int nkb;
+        decode(tile, mt, nt, kbeg, nkb);
+        const int32_t m0 = (int32_t)((mt * NCTA + cta_rank) * kTM);
+        const int32_t n0 = (int32_t)(nt * BN + (int64_t)cta_rank * BNH);
+        for (int kb = 0; kb < nkb; ++kb, ++it) {
+          const int s = it % STAGES;
+          mbar_wait(&empty_bar[s], ((it / STAGES) & 1) ^ 1);
+          uint64_t* bar = &full_bar[s];
+          mbar_expect_tx(bar, (uint32_t)STAGE);
+          const uint32_t st = smem_u32(tiles + (size_t)s * STAGE);
+          const int32_t k0 = (int32_t)(kbeg + (int64_t)kb * kTK);
+          if (g.a_mn) {        // [k, m] planes: one 64(m) x 64(k) box per 64-wide atom
+#pragma unroll
+            for (int j = 0; j < kTM / 64; ++j) {
+              tma_load_2d(st + j * 8192, &tm_ah, m0 + 64 * j, k0, bar);
+              tma_load_2d(st + A_PLANE + j * 8192, &tm_al, m0 + 64 * j, k0, bar);
+            }
+          } else {             // [m, k] planes: one 64(k) x 128(m) box
+            tma_load_2d(st, &tm_ah, k0, m0, bar);
+            tma_load_2d(st + A_PLANE, &tm_al, k0, m0, bar);
+          }
+          if (g.b_mn) {
+#pragma unroll
+            for (int j = 0; j < (BNH >= 64 ? BNH / 64 : 1); ++j) {
+              tma_load_2d(st + 2 * A_PLANE + j * 8192, &tm_bh, n0 + 64 * j, k0, bar);
+              tma_load_2d(st + 2 * A_PLANE + B_PLANE + j * 8192, &tm_bl, n0 + 64 * j, k0, bar);
+            }
+          } else {
+            tma_load_2d(st + 2 * A_PLANE, &tm_bh, k0, n0, bar);
+            tma_load_2d(st + 2 * A_PLANE + B_PLANE, &tm_bl, k0, n0, bar);
+          }
+        }
+      }
+    }
+  } else if (warp >= kWsEpilogueWarps && warp < kMmaWarp) {
     // ------------------------------------------------------------------------------ producers
     const int tid = threadIdx.x - kWsEpilogueWarps * 32;
     constexpr int NT = kWsProducers * 32;
@@ -1035,11 +1101,16 @@ __global__ void __launch_bounds__(kWsThreads, 1) gemm_planes_ws_kernel(const __g
   }
 }
 
-template <int BN, int STAGES, int NCTA>
-static cudaError_t launch_ws(const WsArgs& wa, cudaStream_t st) {
+struct TmaMaps {
+  CUtensorMap ah, al, bh, bl;
+  bool ok;
+};
+
+template <int BN, int STAGES, int NCTA, bool TMA>
+static cudaError_t launch_ws_impl(const WsArgs& wa, const TmaMaps& tm, cudaStream_t st) {
   constexpr size_t smem = (size_t)STAGES * (2 * kTM * 128 + 2 * (BN / NCTA) * 128) + 1024;
   static_assert(smem + 256 <= 227 * 1024, "stage ring exceeds shared memory");
-  auto kern = gemm_planes_ws_kernel<BN, STAGES, NCTA>;
+  auto kern = gemm_planes_ws_kernel<BN, STAGES, NCTA, TMA>;
   cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) return e;
   const int64_t max_clusters = kNumSMs / NCTA;
@@ -1056,7 +1127,47 @@ static cudaError_t launch_ws(const WsArgs& wa, cudaStream_t st) {
   attr[0].val.clusterDim.z = 1;
   cfg.attrs = attr;
   cfg.numAttrs = 1;
-  return cudaLaunchKernelEx(&cfg, kern, wa);
+  return cudaLaunchKernelEx(&cfg, kern, wa, tm.ah, tm.al, tm.bh, tm.bl);
+}
+template <int BN, int STAGES, int NCTA>
+static cudaError_t launch_ws(const WsArgs& wa, const TmaMaps& tm, cudaStream_t st) {
+  return tm.ok ? launch_ws_impl<BN, STAGES, NCTA, true>(wa, tm, st) : launch_ws_impl<BN, STAGES, NCTA, false>(wa, tm, st);
+}
+
+// ---- tensor maps: cuTensorMapEncodeTiled resolved through the runtime's driver entry-point query ---------
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+static EncodeTiledFn tma_encoder() {
+  static EncodeTiledFn fn = nullptr;
+  static bool tried = false;
+  if (!tried) {
+    tried = true;
+    const char* ev = getenv("B2CTR_TC_TMA");
+    if (ev && atoi(ev) == 0) return nullptr;
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess &&
+        q == cudaDriverEntryPointSuccess)
+      fn = (EncodeTiledFn)p;
+    else
+      cudaGetLastError();
+  }
+  return fn;
+}
+// bf16 matrix [outer, inner] with `pitch` elements between rows; box = box_inner x box_outer, 128-byte swizzle,
+// out-of-range box parts read as zero.
+static bool tma_map_2d(CUtensorMap* m, const void* base, int64_t inner, int64_t outer, int64_t pitch,
+                       int box_inner, int box_outer) {
+  EncodeTiledFn enc = tma_encoder();
+  if (!enc || ((uintptr_t)base & 15) || (pitch * 2) % 16 || box_inner * 2 > 128 || box_outer > 256) return false;
+  cuuint64_t dims[2] = {(cuuint64_t)inner, (cuuint64_t)outer};
+  cuuint64_t strides[1] = {(cuuint64_t)pitch * 2};
+  cuuint32_t box[2] = {(cuuint32_t)box_inner, (cuuint32_t)box_outer};
+  cuuint32_t estr[2] = {1, 1};
+  return enc(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), dims, strides, box, estr,
+             CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+             CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
 }
 
 static inline int64_t round_up(int64_t v, int64_t q) { return (v + q - 1) / q * q; }
@@ -1120,6 +1231,7 @@ static b2ctr_status_t gemm_planes(const b2ctr_gemm_t* g, void* workspace, size_t
   const int b_mn = b_given ? !b_kc : ((!b_kc && mn_ok && bn >= 64) ? 1 : 0);   // an MN atom is 64 elements wide
   __nv_bfloat16 *a_hi, *a_lo, *b_hi, *b_lo;
   int64_t a_pitch, b_pitch;
+  int64_t a_prows, b_prows;      // rows of the plane matrices as stored (TMA extents)
   auto split_k = [&](const float* p, int64_t ld, int64_t rows, int64_t cols, int64_t rows_pad, int64_t cols_pad,
                      __nv_bfloat16* hi, __nv_bfloat16* lo) {      // planes[r, c] = p[r*ld + c]
     const int vec = (ld % 4 == 0) && (((uintptr_t)p & 15) == 0);
@@ -1133,10 +1245,10 @@ static b2ctr_status_t gemm_planes(const b2ctr_gemm_t* g, void* workspace, size_t
   };
   if (a_given) {
     const int64_t rp = round_up(a_sr, 256), cp = planes_cols_pad(a_sc);
-    a_hi = (__nv_bfloat16*)g->a_planes; a_lo = a_hi + rp * cp; a_pitch = cp;
+    a_hi = (__nv_bfloat16*)g->a_planes; a_lo = a_hi + rp * cp; a_pitch = cp; a_prows = rp;
   } else {
     a_hi = (__nv_bfloat16*)w; a_lo = a_hi + mp * kp; w = (unsigned char*)(a_lo + mp * kp);
-    a_pitch = a_mn ? mp : kp;
+    a_pitch = a_mn ? mp : kp; a_prows = a_mn ? kp : mp;
     if (a_kc) split_k(g->a, g->lda, g->m, g->k, mp, kp, a_hi, a_lo);
     else if (a_mn) split_k(g->a, g->lda, g->k, g->m, kp, mp, a_hi, a_lo);
     else split_t(g->a, g->lda, g->m, mp, a_hi, a_lo);
@@ -1144,10 +1256,10 @@ static b2ctr_status_t gemm_planes(const b2ctr_gemm_t* g, void* workspace, size_t
   }
   if (b_given) {
     const int64_t rp = round_up(b_sr, 256), cp = planes_cols_pad(b_sc);
-    b_hi = (__nv_bfloat16*)g->b_planes; b_lo = b_hi + rp * cp; b_pitch = cp;
+    b_hi = (__nv_bfloat16*)g->b_planes; b_lo = b_hi + rp * cp; b_pitch = cp; b_prows = rp;
   } else {
     b_hi = (__nv_bfloat16*)w; b_lo = b_hi + np * kp;
-    b_pitch = b_mn ? np : kp;
+    b_pitch = b_mn ? np : kp; b_prows = b_mn ? kp : np;
     if (b_kc) split_k(g->b, g->ldb, g->n, g->k, np, kp, b_hi, b_lo);
     else if (b_mn) split_k(g->b, g->ldb, g->k, g->n, kp, np, b_hi, b_lo);
     else split_t(g->b, g->ldb, g->n, np, b_hi, b_lo);
@@ -1171,16 +1283,23 @@ static b2ctr_status_t gemm_planes(const b2ctr_gemm_t* g, void* workspace, size_t
     wa.tiles_m = (int)ceil_div(g->m, (int64_t)kTM * ncta);
     wa.tiles_n = (int)ceil_div(g->n, bn);
     wa.ntiles = (int64_t)wa.tiles_m * wa.tiles_n * splits;
+    // TMA producers: four tiled tensor maps over the operand planes (box = one stage's slice of a plane)
+    TmaMaps tm;
+    const int bnh = bn / ncta;
+    tm.ok = tma_map_2d(&tm.ah, a_hi, a_pitch, a_prows, a_pitch, 64, a_mn ? 64 : kTM) &&
+            tma_map_2d(&tm.al, a_lo, a_pitch, a_prows, a_pitch, 64, a_mn ? 64 : kTM) &&
+            tma_map_2d(&tm.bh, b_hi, b_pitch, b_prows, b_pitch, 64, b_mn ? 64 : bnh) &&
+            tma_map_2d(&tm.bl, b_lo, b_pitch, b_prows, b_pitch, 64, b_mn ? 64 : bnh);
     if (ncta == 2) {
-      if (bn == 32) e = launch_ws<32, 5, 2>(wa, st);
-      else if (bn == 64) e = launch_ws<64, 5, 2>(wa, st);
-      else if (bn == 128) e = launch_ws<128, 4, 2>(wa, st);
-      else e = launch_ws<256, 3, 2>(wa, st);
+      if (bn == 32) e = launch_ws<32, 5, 2>(wa, tm, st);
+      else if (bn == 64) e = launch_ws<64, 5, 2>(wa, tm, st);
+      else if (bn == 128) e = launch_ws<128, 4, 2>(wa, tm, st);
+      else e = launch_ws<256, 3, 2>(wa, tm, st);
     } else {
-      if (bn == 32) e = launch_ws<32, 5, 1>(wa, st);
-      else if (bn == 64) e = launch_ws<64, 4, 1>(wa, st);
-      else if (bn == 128) e = launch_ws<128, 3, 1>(wa, st);
-      else e = launch_ws<256, 2, 1>(wa, st);
+      if (bn == 32) e = launch_ws<32, 5, 1>(wa, tm, st);
+      else if (bn == 64) e = launch_ws<64, 4, 1>(wa, tm, st);
+      else if (bn == 128) e = launch_ws<128, 3, 1>(wa, tm, st);
+      else e = launch_ws<256, 2, 1>(wa, tm, st);
     }
   } else if (bn == 32) e = short_k ? launch_planes<32, 1>(pa, st) : launch_planes<32, 4>(pa, st);
   else if (bn == 64) e = short_k ? launch_planes<64, 1>(pa, st) : launch_planes<64, 4>(pa, st);

@@ -158,6 +158,14 @@ typedef struct b2ctr_uniform_gather {
    * F*dim + ndense <= x_planes_cols <= x_cols.  NULL = off. */
   void* x_planes;
   int64_t x_planes_cols;
+  /* Optional persisting-L2 window (cudaAccessPolicyWindow attached to THIS launch): [l2_window, l2_window +
+   * l2_window_bytes) - the arena holding the dim-1 linear tables (26 x 1M x 4 B = 104 MB at C2, inside the
+   * 126 MB L2) - is fetched with the persisting property for a fraction l2_hit_ratio of its lines, everything
+   * else streams.  Each 4-byte linear lookup otherwise costs a 64-byte DRAM granule in the gather and two in
+   * the update.  Needs b2ctr_l2_persist_reserve() once per device.  NULL / 0 = off. */
+  const void* l2_window;
+  int64_t l2_window_bytes;
+  float l2_hit_ratio;
 } b2ctr_uniform_gather_t;
 /* scatter_uniform_bwd: every (sample, feature) id is distinct (the ids are positions in a private row
  * buffer, as on the row-sharded path): write scale*g instead of accumulating, no zero-fill needed. */
@@ -165,6 +173,11 @@ typedef struct b2ctr_uniform_gather {
 
 B2CTR_API b2ctr_status_t b2ctr_embed_gather_uniform_fwd(const b2ctr_uniform_gather_t* g,
                                                        int64_t batch, void* stream);
+
+/* Set aside up to `bytes` of the current device's L2 for persisting accesses (cudaLimitPersistingL2CacheSize,
+ * clamped to the device maximum).  *granted = the set-aside size, *max_window = the largest access-policy
+ * window the device accepts.  bytes = 0 releases the set-aside. */
+B2CTR_API b2ctr_status_t b2ctr_l2_persist_reserve(int64_t bytes, int64_t* granted, int64_t* max_window);
 
 /* Backward of the above fused with the row update:
  *   g_row(b,f) = dx[b, f*dim:(f+1)*dim] + dfm[b] * (S_b - x[b, f*dim:...])   (FM Jacobian, App. A.6)

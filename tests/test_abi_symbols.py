@@ -30,7 +30,7 @@ def test_struct_layouts_match_header():
     assert ctypes.sizeof(L.Feature) == 112
     assert L.Feature.src_table.offset == 96
     assert ctypes.sizeof(L.Gemm) == 128
-    assert ctypes.sizeof(L.UniformGather) == 136
+    assert ctypes.sizeof(L.UniformGather) == 160
 
 
 def test_kernels_refuse_cpu_tensors():

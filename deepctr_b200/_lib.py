@@ -63,6 +63,22 @@ class Gemm(C.Structure):
                 ("alpha", C.c_float), ("variant", C.c_int32), ("a_planes", C.c_void_p), ("b_planes", C.c_void_p)]
 
 
+class CinGemm(C.Structure):
+    """b2ctr_cin_gemm_t"""
+    _fields_ = [("t0", C.c_void_p), ("ld0", C.c_int64), ("xk", C.c_void_p), ("ldk", C.c_int64), ("rows", C.c_int64),
+                ("m", C.c_int32), ("h", C.c_int32), ("hp", C.c_int32), ("n", C.c_int32),
+                ("w_planes", C.c_void_p), ("dy_planes", C.c_void_p), ("c", C.c_void_p), ("ldc", C.c_int64),
+                ("bias", C.c_void_p), ("act", C.c_int32), ("mode", C.c_int32), ("split_k", C.c_int32)]
+
+
+class AttGemm(C.Structure):
+    """b2ctr_att_gemm_t"""
+    _fields_ = [("query", C.c_void_p), ("ldq", C.c_int64), ("keys", C.c_void_p), ("key_batch_stride", C.c_int64),
+                ("batch", C.c_int64), ("maxlen", C.c_int32), ("dim", C.c_int32), ("n", C.c_int32),
+                ("planes", C.c_void_p), ("c", C.c_void_p), ("ldc", C.c_int64), ("bias", C.c_void_p),
+                ("act", C.c_int32), ("mode", C.c_int32), ("split_k", C.c_int32)]
+
+
 _vp, _i32, _i64, _f32, _sz, _u64 = C.c_void_p, C.c_int32, C.c_int64, C.c_float, C.c_size_t, C.c_uint64
 
 # name -> (restype, argtypes).  Must list every symbol of include/b2ctr.h (tests check this).
@@ -77,6 +93,9 @@ SIGNATURES = {
     "b2ctr_embed_scatter_uniform_bwd": (_i32, [C.POINTER(UniformGather), _vp, _vp, _vp, _f32, _f32,
                                                _i64, _vp]),
     "b2ctr_embed_oob_count": (_i32, [C.POINTER(C.c_int64), _i32, _vp]),
+    "b2ctr_embed_update_sorted_workspace_bytes": (_sz, [_i32, _i32, _i64]),
+    "b2ctr_embed_update_sorted": (_i32, [C.POINTER(UniformGather), _vp, _vp, _vp, _i32, _f32, _f32, _f32,
+                                         C.POINTER(C.c_void_p), C.POINTER(C.c_void_p), _i64, _vp, _sz, _vp]),
     "b2ctr_hash64": (_i32, [_vp, _i32, _i64, _i64, _i32, _vp, _vp]),
     "b2ctr_init_normal": (_i32, [_vp, _i64, _f32, _f32, _u64, _vp]),
     "b2ctr_gemm_workspace_bytes": (_sz, [C.POINTER(Gemm)]),
@@ -114,7 +133,15 @@ SIGNATURES = {
     "b2ctr_cin_outer_fwd": (_i32, [_vp, _i64, _i64, _i64, _vp, _i64, _i64, _i64, _vp, _i64, _i32, _i32, _i32,
                                    _vp]),
     "b2ctr_cin_outer_bwd": (_i32, [_vp, _vp, _i64, _i64, _i64, _vp, _i64, _i64, _i64, _vp, _i64, _i64, _i64,
-                                   _i32, _vp, _i64, _i64, _i64, _i32, _i64, _i32, _i32, _i32, _vp]),
+                                   _i32, _vp, _i64, _i64, _i64, _i32, _i64, _i32, _i32, _i32, _i32, _vp]),
+    "b2ctr_cin_filter_planes_bytes": (_sz, [_i32, _i32, _i64]),
+    "b2ctr_cin_filter_planes": (_i32, [_vp, _i32, _i32, _i32, _i64, _vp, _vp]),
+    "b2ctr_cin_gemm_workspace_bytes": (_sz, [C.POINTER(CinGemm)]),
+    "b2ctr_cin_gemm": (_i32, [C.POINTER(CinGemm), _vp, _sz, _vp]),
+    "b2ctr_att_gemm_workspace_bytes": (_sz, [C.POINTER(AttGemm)]),
+    "b2ctr_att_gemm": (_i32, [C.POINTER(AttGemm), _vp, _sz, _vp]),
+    "b2ctr_cin_t0": (_i32, [_vp, _i64, _i64, _i64, _vp, _i64, _i64, _i32, _i32, _vp]),
+    "b2ctr_cin_unpad_rows": (_i32, [_vp, _vp, _i32, _i32, _i32, _i64, _vp]),
     "b2ctr_cin_sum_d": (_i32, [_vp, _i64, _i32, _i32, _i32, _vp, _i64, _i32, _i64, _vp]),
     "b2ctr_cin_expand_grad": (_i32, [_vp, _i64, _i32, _i32, _i32, _vp, _i64, _i32, _vp, _i64, _i32, _i64, _vp]),
     "b2ctr_interacting_fwd": (_i32, [_vp, _vp, _vp, _vp, _vp, _i64, _i32, _i32, _i32, _i32, _vp]),

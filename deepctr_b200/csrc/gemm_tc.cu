@@ -370,6 +370,13 @@ struct PlaneArgs {
   int64_t k_per_split;
   float alpha;
   int act, accumulate, splits;
+  // CIN mode (cin_on): the A operand is never stored anywhere - the producer warps GENERATE its bf16 hi/lo tile
+  // in shared memory from the two factors of the outer product (deepctr/layers/interaction.py:287-297):
+  //   A[r, i*hp + j] = t0[r*ld0 + i] * xk[r*ldk + j]   (j < h, i < m; zero otherwise),  r = (sample, embedding dim)
+  // a_mn = 0: A is [rows, m*hp] (forward, M = r);  a_mn = 1: A^T, i.e. M = i*hp + j and K = r (filter gradient).
+  const float* cin_t0; const float* cin_xk;
+  int64_t cin_ld0, cin_ldk, cin_rows;
+  int cin_m, cin_h, cin_hp, cin_on;
 };
 
 // dst planes [rows_pad, k_pad] <- src(r, k) = p[r*sr + k*sk]; zero outside [rows, k).
@@ -755,7 +762,100 @@ __device__ __forceinline__ void tma_prefetch_desc(const CUtensorMap* map) {
   asm volatile("prefetch.tensormap [%0];" ::"l"(map) : "memory");
 }
 
-template <int BN, int STAGES, int NCTA, bool TMA>
+// One producer thread = one row r of the outer product: 64 consecutive q = i*hp + j starting at q0 (hp is 32 or a
+// multiple of 64, so 8-element chunks never straddle an i), split into bf16 hi/lo and stored as eight 16-byte
+// chunks of the 128-byte-swizzled row `rr` of the stage (rr & 7 selects the XOR pattern).
+__device__ __forceinline__ void cin_generate_row(const PlaneArgs& g, int64_t r, int64_t q0, unsigned char* hi_row,
+                                                 unsigned char* lo_row, int rr) {
+  const bool row_ok = r < g.cin_rows;
+  const float* xk = g.cin_xk + r * g.cin_ldk;
+  const float* t0 = g.cin_t0 + r * g.cin_ld0;
+#pragma unroll
+  for (int c = 0; c < 8; ++c) {
+    const int64_t q = q0 + 8 * c;
+    const int i = (int)(q / g.cin_hp), j = (int)(q - (int64_t)i * g.cin_hp);
+    float v[8];
+    if (row_ok && i < g.cin_m && j < g.cin_h) {
+      const float a = __ldg(t0 + i);
+      // h % 4 == 0 and j % 8 == 0: the first quad is inside the row whenever j < h; the second may not be
+      const float4 x0 = __ldg(reinterpret_cast<const float4*>(xk + j));
+      const float4 x1 = j + 4 < g.cin_h ? __ldg(reinterpret_cast<const float4*>(xk + j) + 1) : make_float4(0.f, 0.f, 0.f, 0.f);
+      v[0] = a * x0.x; v[1] = a * x0.y; v[2] = a * x0.z; v[3] = a * x0.w;
+      v[4] = a * x1.x; v[5] = a * x1.y; v[6] = a * x1.z; v[7] = a * x1.w;
+#pragma unroll
+      for (int e = 0; e < 8; ++e)
+        if (j + e >= g.cin_h) v[e] = 0.f;
+    } else {
+#pragma unroll
+      for (int e = 0; e < 8; ++e) v[e] = 0.f;
+    }
+    uint32_t h[4], l[4];
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+      const __nv_bfloat16 h0 = __float2bfloat16_rn(v[2 * e]), h1 = __float2bfloat16_rn(v[2 * e + 1]);
+      h[e] = pack_bf16(h0, h1);
+      l[e] = pack_bf16(__float2bfloat16_rn(v[2 * e] - __bfloat162float(h0)),
+                       __float2bfloat16_rn(v[2 * e + 1] - __bfloat162float(h1)));
+    }
+    const int off = (c ^ (rr & 7)) << 4;
+    *reinterpret_cast<uint4*>(hi_row + off) = make_uint4(h[0], h[1], h[2], h[3]);
+    *reinterpret_cast<uint4*>(lo_row + off) = make_uint4(l[0], l[1], l[2], l[3]);
+  }
+}
+
+// DIN local-activation-unit input (deepctr/layers/core.py:96-101), generated the same way: row r = (b, t),
+//   A[r, :] = [ q_b , k_bt , q_b - k_bt , q_b * k_bt ]   (4 segments of E columns; E % 8 == 0)
+// cin_t0 = queries [B, ld0], cin_xk = keys (sample stride cin_ldk, row stride E), cin_m = T, cin_h = E.
+__device__ __forceinline__ void att_generate_row(const PlaneArgs& g, int64_t r, int64_t c0, unsigned char* hi_row,
+                                                 unsigned char* lo_row, int rr) {
+  const int T = g.cin_m, E = g.cin_h;
+  const bool row_ok = r < g.cin_rows;
+  const int64_t b = row_ok ? r / T : 0;
+  const int t = row_ok ? (int)(r - b * T) : 0;
+  const float* q = g.cin_t0 + b * g.cin_ld0;
+  const float* k = g.cin_xk + b * g.cin_ldk + (int64_t)t * E;
+#pragma unroll
+  for (int c = 0; c < 8; ++c) {
+    const int64_t col = c0 + 8 * c;
+    const int seg = (int)(col / E), e = (int)(col - (int64_t)seg * E);
+    float v[8];
+    if (row_ok && seg < 4) {
+      float qa[8], ka[8];
+      if (seg != 1) {
+        const float4 a0 = __ldg(reinterpret_cast<const float4*>(q + e)), a1 = __ldg(reinterpret_cast<const float4*>(q + e) + 1);
+        qa[0] = a0.x; qa[1] = a0.y; qa[2] = a0.z; qa[3] = a0.w; qa[4] = a1.x; qa[5] = a1.y; qa[6] = a1.z; qa[7] = a1.w;
+      }
+      if (seg != 0) {
+        const float4 b0 = __ldg(reinterpret_cast<const float4*>(k + e)), b1 = __ldg(reinterpret_cast<const float4*>(k + e) + 1);
+        ka[0] = b0.x; ka[1] = b0.y; ka[2] = b0.z; ka[3] = b0.w; ka[4] = b1.x; ka[5] = b1.y; ka[6] = b1.z; ka[7] = b1.w;
+      }
+#pragma unroll
+      for (int j = 0; j < 8; ++j)
+        v[j] = seg == 0 ? qa[j] : seg == 1 ? ka[j] : seg == 2 ? __fsub_rn(qa[j], ka[j]) : __fmul_rn(qa[j], ka[j]);
+    } else {
+#pragma unroll
+      for (int j = 0; j < 8; ++j) v[j] = 0.f;
+    }
+    uint32_t h[4], l[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const __nv_bfloat16 h0 = __float2bfloat16_rn(v[2 * j]), h1 = __float2bfloat16_rn(v[2 * j + 1]);
+      h[j] = pack_bf16(h0, h1);
+      l[j] = pack_bf16(__float2bfloat16_rn(v[2 * j] - __bfloat162float(h0)),
+                       __float2bfloat16_rn(v[2 * j + 1] - __bfloat162float(h1)));
+    }
+    const int off = (c ^ (rr & 7)) << 4;
+    *reinterpret_cast<uint4*>(hi_row + off) = make_uint4(h[0], h[1], h[2], h[3]);
+    *reinterpret_cast<uint4*>(lo_row + off) = make_uint4(l[0], l[1], l[2], l[3]);
+  }
+}
+__device__ __forceinline__ void generate_row(const PlaneArgs& g, int64_t r, int64_t q0, unsigned char* hi_row,
+                                             unsigned char* lo_row, int rr) {
+  if (g.cin_on == 2) att_generate_row(g, r, q0, hi_row, lo_row, rr);
+  else cin_generate_row(g, r, q0, hi_row, lo_row, rr);
+}
+
+template <int BN, int STAGES, int NCTA, bool TMA, bool CIN = false>
 __global__ void __launch_bounds__(kWsThreads, 1)
     gemm_planes_ws_kernel(const __grid_constant__ WsArgs w, const __grid_constant__ CUtensorMap tm_ah,
                           const __grid_constant__ CUtensorMap tm_al, const __grid_constant__ CUtensorMap tm_bh,
@@ -779,7 +879,8 @@ __global__ void __launch_bounds__(kWsThreads, 1)
   if (threadIdx.x == 0) {
     for (int s = 0; s < STAGES; ++s) {
       // cp.async producers: one deferred arrival per producer thread of THIS CTA; TMA: one arrive.expect_tx
-      mbar_init(&full_bar[s], TMA ? 1 : kWsProducers * 32);
+      // CIN: the B planes arrive by TMA (1 arrive.expect_tx) + one arrival per generating thread
+      mbar_init(&full_bar[s], CIN ? 1 + kWsProducers * 32 : (TMA ? 1 : kWsProducers * 32));
       mbar_init(&peer_full[s], 1);                    // leader only: the peer CTA's half of the stage landed
       mbar_init(&empty_bar[s], 1);
     }
@@ -820,7 +921,50 @@ __global__ void __launch_bounds__(kWsThreads, 1)
   };
 
   constexpr int kMmaWarp = kWsEpilogueWarps + kWsProducers;
-  if (TMA && warp >= kWsEpilogueWarps && warp < kMmaWarp) {
+  if (CIN && warp >= kWsEpilogueWarps && warp < kMmaWarp) {
+    // ------------------------------------------------------------------------------ CIN producers
+    // B (filter / dY planes) by TMA from thread 0; A generated in place by all 128 producer threads.
+    const int tid = threadIdx.x - kWsEpilogueWarps * 32;
+    if (tid == 0) { tma_prefetch_desc(&tm_bh); tma_prefetch_desc(&tm_bl); }
+    uint32_t it = 0;
+    for (int64_t tile = cluster_id; tile < w.ntiles; tile += nclusters) {
+      int64_t mt, nt, kbeg;
+      int nkb;
+      decode(tile, mt, nt, kbeg, nkb);
+      const int64_t m0 = (mt * NCTA + cta_rank) * kTM;
+      const int32_t n0 = (int32_t)(nt * BN + (int64_t)cta_rank * BNH);
+      for (int kb = 0; kb < nkb; ++kb, ++it) {
+        const int s = it % STAGES;
+        mbar_wait(&empty_bar[s], ((it / STAGES) & 1) ^ 1);
+        unsigned char* stp = tiles + (size_t)s * STAGE;
+        const int64_t k0 = kbeg + (int64_t)kb * kTK;
+        if (tid == 0) {
+          uint64_t* bar = &full_bar[s];
+          mbar_expect_tx(bar, (uint32_t)(2 * B_PLANE));
+          const uint32_t st = smem_u32(stp);
+          if (g.b_mn) {
+#pragma unroll
+            for (int j = 0; j < (BNH >= 64 ? BNH / 64 : 1); ++j) {
+              tma_load_2d(st + 2 * A_PLANE + j * 8192, &tm_bh, n0 + 64 * j, (int32_t)k0, bar);
+              tma_load_2d(st + 2 * A_PLANE + B_PLANE + j * 8192, &tm_bl, n0 + 64 * j, (int32_t)k0, bar);
+            }
+          } else {
+            tma_load_2d(st + 2 * A_PLANE, &tm_bh, (int32_t)k0, n0, bar);
+            tma_load_2d(st + 2 * A_PLANE + B_PLANE, &tm_bl, (int32_t)k0, n0, bar);
+          }
+        }
+        if (g.a_mn) {      // A^T: M = q (two 64-wide atoms), K = r: thread -> (atom, k-row)
+          const int atom = tid >> 6, rr = tid & 63;
+          generate_row(g, k0 + rr, m0 + atom * 64, stp + atom * 8192 + rr * 128,
+                       stp + A_PLANE + atom * 8192 + rr * 128, rr);
+        } else {           // A: M = r, K = q: thread -> row
+          generate_row(g, m0 + tid, k0, stp + tid * 128, stp + A_PLANE + tid * 128, tid);
+        }
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+        mbar_arrive(&full_bar[s]);
+      }
+    }
+  } else if (TMA && warp >= kWsEpilogueWarps && warp < kMmaWarp) {
     // ------------------------------------------------------------------------------ TMA producer
     // warp 8, one elected lane: wait for a free stage, arm its barrier with the stage bytes, issue the bulk
     // tensor copies of the four operand planes.  No registers, no per-element instructions, no proxy fence:
@@ -1106,11 +1250,11 @@ struct TmaMaps {
   bool ok;
 };
 
-template <int BN, int STAGES, int NCTA, bool TMA>
+template <int BN, int STAGES, int NCTA, bool TMA, bool CIN = false>
 static cudaError_t launch_ws_impl(const WsArgs& wa, const TmaMaps& tm, cudaStream_t st) {
   constexpr size_t smem = (size_t)STAGES * (2 * kTM * 128 + 2 * (BN / NCTA) * 128) + 1024;
   static_assert(smem + 256 <= 227 * 1024, "stage ring exceeds shared memory");
-  auto kern = gemm_planes_ws_kernel<BN, STAGES, NCTA, TMA>;
+  auto kern = gemm_planes_ws_kernel<BN, STAGES, NCTA, TMA, CIN>;
   cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) return e;
   const int64_t max_clusters = kNumSMs / NCTA;
@@ -1273,6 +1417,7 @@ static b2ctr_status_t gemm_planes(const b2ctr_gemm_t* g, void* workspace, size_t
   pa.m = g->m; pa.n = g->n; pa.k_pad = kp; pa.ldc = g->ldc;
   pa.k_per_split = ceil_div(ceil_div(kp, splits), kTK) * kTK;
   pa.alpha = g->alpha; pa.act = g->act; pa.accumulate = g->accumulate; pa.splits = splits;
+  pa.cin_on = 0; pa.cin_t0 = pa.cin_xk = nullptr; pa.cin_ld0 = pa.cin_ldk = pa.cin_rows = 0; pa.cin_m = pa.cin_h = pa.cin_hp = 0;
   cudaError_t e;
   const bool short_k = pa.k_per_split <= 4 * kTK;
   if (ws_kernel) {
@@ -1318,6 +1463,165 @@ static b2ctr_status_t gemm_planes(const b2ctr_gemm_t* g, void* workspace, size_t
     B2_CHECK_LAUNCH("b2ctr_gemm(bf16x3 splitk_reduce)");
   }
   return B2CTR_OK;
+}
+
+// ================================================================================================
+// CIN on the tensor cores without ever materialising the outer product.
+// ================================================================================================
+// planes of the PADDED filter W'[i*hp + j, n] = W[i*h + j, n] (j < h), zero rows for h <= j < hp
+__global__ void __launch_bounds__(256)
+    cin_filter_planes_kernel(const float* __restrict__ w, int m, int h, int hp, int64_t n, int64_t rows_pad,
+                             int64_t cols_pad, __nv_bfloat16* hi, __nv_bfloat16* lo) {
+  const int64_t chunks = cols_pad / 8;
+  const int64_t total = rows_pad * chunks;
+  for (int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; t < total; t += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t r = t / chunks;
+    const int64_t c0 = (t - r * chunks) * 8;
+    const int i = (int)(r / hp), j = (int)(r - (int64_t)i * hp);
+    const bool ok = i < m && j < h;
+    uint32_t hh[4], ll[4];
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+      const float v0 = (ok && c0 + 2 * e < n) ? __ldg(w + ((int64_t)i * h + j) * n + c0 + 2 * e) : 0.f;
+      const float v1 = (ok && c0 + 2 * e + 1 < n) ? __ldg(w + ((int64_t)i * h + j) * n + c0 + 2 * e + 1) : 0.f;
+      const __nv_bfloat16 h0 = __float2bfloat16_rn(v0), h1 = __float2bfloat16_rn(v1);
+      hh[e] = pack_bf16(h0, h1);
+      ll[e] = pack_bf16(__float2bfloat16_rn(v0 - __bfloat162float(h0)), __float2bfloat16_rn(v1 - __bfloat162float(h1)));
+    }
+    *reinterpret_cast<uint4*>(hi + r * cols_pad + c0) = make_uint4(hh[0], hh[1], hh[2], hh[3]);
+    *reinterpret_cast<uint4*>(lo + r * cols_pad + c0) = make_uint4(ll[0], ll[1], ll[2], ll[3]);
+  }
+}
+
+b2ctr_status_t cin_filter_planes(const float* w, int m, int h, int hp, int64_t n, void* planes, cudaStream_t st) {
+  const int64_t rp = round_up((int64_t)m * hp, 256), cp = planes_cols_pad(n);
+  __nv_bfloat16* hi = (__nv_bfloat16*)planes;
+  cin_filter_planes_kernel<<<grid_for(rp * (cp / 8), 256, 8), 256, 0, st>>>(w, m, h, hp, n, rp, cp, hi, hi + rp * cp);
+  B2_CHECK_LAUNCH("b2ctr_cin_filter_planes");
+  return B2CTR_OK;
+}
+
+// A GEMM whose A operand is generated by the producer warps (kind 1: CIN outer product, kind 2: DIN attention input)
+struct GenSpec {
+  int kind;
+  const float* p0; int64_t ld0;
+  const float* p1; int64_t ld1;
+  int64_t rows;
+  int m, h, hp;
+  int64_t kq;            // columns of the generated matrix
+};
+
+static size_t gen_gemm_workspace_bytes(const GenSpec& sp, int mode, int64_t n, int split_k) {
+  const int64_t M = mode == 0 ? sp.rows : sp.kq;
+  return split_k > 1 ? (size_t)split_k * M * n * sizeof(float) + 256 : 0;
+}
+
+// mode 0: c[rows, n] = act(A B + bias), B = planes of a [kq, n] row-major matrix; mode 1: c[kq, n] = A^T dY,
+// dY given as the planes of a [rows, n] row-major matrix.
+static b2ctr_status_t gen_gemm(const GenSpec& sp, int mode, int64_t n, const void* planes, float* c, int64_t ldc,
+                               const float* bias, int act, int split_k, void* workspace, size_t workspace_bytes,
+                               cudaStream_t st, const char* what) {
+  const size_t need = gen_gemm_workspace_bytes(sp, mode, n, split_k);
+  if (need && (!workspace || workspace_bytes < need)) {
+    set_error("%s: needs %zu workspace bytes, got %zu", what, need, workspace_bytes);
+    return B2CTR_ERR_WORKSPACE;
+  }
+  const int splits = split_k > 1 ? split_k : 1;
+  PlaneArgs pa;
+  pa.a_hi = pa.a_lo = nullptr; pa.a_pitch = 0;
+  pa.cin_on = sp.kind; pa.cin_t0 = sp.p0; pa.cin_xk = sp.p1; pa.cin_ld0 = sp.ld0; pa.cin_ldk = sp.ld1;
+  pa.cin_rows = sp.rows; pa.cin_m = sp.m; pa.cin_h = sp.h; pa.cin_hp = sp.hp;
+  pa.b_mn = 1;      // both B operands are row-major matrices whose reduction dim is their row index
+  pa.c = c; pa.bias = bias; pa.ws = (float*)workspace; pa.ldc = ldc;
+  pa.alpha = 1.f; pa.act = act; pa.accumulate = 0; pa.splits = splits;
+  pa.n = n;
+  const int64_t cp = planes_cols_pad(n);
+  int64_t b_prows;
+  if (mode == 0) {
+    pa.a_mn = 0; pa.m = sp.rows; pa.k_pad = round_up(sp.kq, kTK);
+    b_prows = round_up(sp.kq, 256);
+  } else {
+    pa.a_mn = 1; pa.m = sp.kq; pa.k_pad = round_up(sp.rows, kTK);
+    b_prows = round_up(sp.rows, 256);
+  }
+  const __nv_bfloat16* bp = (const __nv_bfloat16*)planes;
+  pa.b_hi = bp; pa.b_lo = bp + b_prows * cp; pa.b_pitch = cp;
+  pa.k_per_split = ceil_div(ceil_div(pa.k_pad, splits), kTK) * kTK;
+  const int bn = n <= 64 ? 64 : (n <= 128 ? 128 : 256);
+  int ncta = pa.m > kTM ? 2 : 1;
+  if (bn / ncta < 64) ncta = 1;
+  WsArgs wa;
+  wa.p = pa;
+  wa.tiles_m = (int)ceil_div(pa.m, (int64_t)kTM * ncta);
+  wa.tiles_n = (int)ceil_div(n, bn);
+  wa.ntiles = (int64_t)wa.tiles_m * wa.tiles_n * splits;
+  TmaMaps tm;
+  tm.ok = tma_map_2d(&tm.bh, pa.b_hi, cp, b_prows, cp, 64, 64) && tma_map_2d(&tm.bl, pa.b_lo, cp, b_prows, cp, 64, 64);
+  if (!tm.ok) {
+    set_error("%s: cuTensorMapEncodeTiled unavailable (the kernel loads its B operand by TMA)", what);
+    return B2CTR_ERR_UNSUPPORTED;
+  }
+  tm.ah = tm.bh; tm.al = tm.bl;
+  cudaError_t e;
+  if (ncta == 2) {
+    if (bn == 128) e = launch_ws_impl<128, 4, 2, true, true>(wa, tm, st);
+    else e = launch_ws_impl<256, 3, 2, true, true>(wa, tm, st);
+  } else {
+    if (bn == 64) e = launch_ws_impl<64, 4, 1, true, true>(wa, tm, st);
+    else if (bn == 128) e = launch_ws_impl<128, 3, 1, true, true>(wa, tm, st);
+    else e = launch_ws_impl<256, 2, 1, true, true>(wa, tm, st);
+  }
+  if (e != cudaSuccess) {
+    set_error("%s: CUDA launch failed: %s", what, cudaGetErrorString(e));
+    return B2CTR_ERR_CUDA;
+  }
+  count_launch();
+  if (splits > 1) {
+    TcArgs ta;
+    ta.c = c; ta.bias = bias; ta.ws = pa.ws; ta.m = pa.m; ta.n = n; ta.ldc = ldc;
+    ta.act = act; ta.accumulate = 0; ta.splits = splits;
+    tc_splitk_reduce_kernel<<<grid_for(pa.m * n, 256, 4), 256, 0, st>>>(ta);
+    B2_CHECK_LAUNCH("generated-operand gemm (splitk_reduce)");
+  }
+  return B2CTR_OK;
+}
+
+static GenSpec cin_spec(const b2ctr_cin_gemm_t* g) {
+  GenSpec sp;
+  sp.kind = 1; sp.p0 = g->t0; sp.ld0 = g->ld0; sp.p1 = g->xk; sp.ld1 = g->ldk; sp.rows = g->rows;
+  sp.m = g->m; sp.h = g->h; sp.hp = g->hp; sp.kq = (int64_t)g->m * g->hp;
+  return sp;
+}
+size_t cin_gemm_workspace_bytes(const b2ctr_cin_gemm_t* g) {
+  return gen_gemm_workspace_bytes(cin_spec(g), g->mode, g->n, g->split_k);
+}
+b2ctr_status_t cin_gemm(const b2ctr_cin_gemm_t* g, void* workspace, size_t workspace_bytes, cudaStream_t st) {
+  B2_REQUIRE(g && g->t0 && g->xk && g->c && g->rows > 0 && g->m > 0 && g->h > 0 && g->n > 0, "cin_gemm: bad arguments");
+  B2_REQUIRE(g->hp >= g->h && (g->hp == 32 || g->hp % 64 == 0), "cin_gemm: hp must be 32 or a multiple of 64 and >= h");
+  B2_REQUIRE(g->ldk % 4 == 0 && ((uintptr_t)g->xk & 15) == 0 && g->ld0 >= g->m, "cin_gemm: xk rows must be 16-byte aligned");
+  B2_REQUIRE(g->h % 4 == 0 || g->ldk >= g->hp, "cin_gemm: h must be a multiple of 4 unless the xk rows are padded to hp");
+  B2_REQUIRE(g->mode == 0 ? g->w_planes != nullptr : g->dy_planes != nullptr, "cin_gemm: operand planes missing");
+  return gen_gemm(cin_spec(g), g->mode, g->n, g->mode == 0 ? g->w_planes : g->dy_planes, g->c, g->ldc, g->bias, g->act,
+                  g->split_k, workspace, workspace_bytes, st, "b2ctr_cin_gemm");
+}
+
+static GenSpec att_spec(const b2ctr_att_gemm_t* g) {
+  GenSpec sp;
+  sp.kind = 2; sp.p0 = g->query; sp.ld0 = g->ldq; sp.p1 = g->keys; sp.ld1 = g->key_batch_stride;
+  sp.rows = g->batch * g->maxlen; sp.m = g->maxlen; sp.h = g->dim; sp.hp = g->dim; sp.kq = 4 * (int64_t)g->dim;
+  return sp;
+}
+size_t att_gemm_workspace_bytes(const b2ctr_att_gemm_t* g) {
+  return gen_gemm_workspace_bytes(att_spec(g), g->mode, g->n, g->split_k);
+}
+b2ctr_status_t att_gemm(const b2ctr_att_gemm_t* g, void* workspace, size_t workspace_bytes, cudaStream_t st) {
+  B2_REQUIRE(g && g->query && g->keys && g->c && g->planes && g->batch > 0 && g->maxlen > 0 && g->n > 0,
+             "att_gemm: bad arguments");
+  B2_REQUIRE(g->dim > 0 && g->dim % 8 == 0, "att_gemm: the embedding size must be a multiple of 8");
+  B2_REQUIRE(g->ldq % 4 == 0 && g->key_batch_stride % 4 == 0 && ((uintptr_t)g->query & 15) == 0 &&
+                 ((uintptr_t)g->keys & 15) == 0, "att_gemm: query / keys rows must be 16-byte aligned");
+  return gen_gemm(att_spec(g), g->mode, g->n, g->planes, g->c, g->ldc, g->bias, g->act, g->split_k, workspace,
+                  workspace_bytes, st, "b2ctr_att_gemm");
 }
 
 size_t planes_bytes(int64_t rows, int64_t cols) {
@@ -1382,3 +1686,20 @@ b2ctr_status_t gemm_bf16x3(const b2ctr_gemm_t* g, void* workspace, size_t worksp
 }
 
 }  // namespace b2ctr
+
+extern "C" {
+size_t b2ctr_cin_filter_planes_bytes(int32_t m, int32_t hp, int64_t n) { return b2ctr::planes_bytes((int64_t)m * hp, n); }
+b2ctr_status_t b2ctr_cin_filter_planes(const float* w, int32_t m, int32_t h, int32_t hp, int64_t n, void* planes,
+                                       void* stream) {
+  B2_REQUIRE(w && planes && m > 0 && h > 0 && hp >= h && n > 0, "cin_filter_planes: bad arguments");
+  return b2ctr::cin_filter_planes(w, m, h, hp, n, planes, (cudaStream_t)stream);
+}
+size_t b2ctr_cin_gemm_workspace_bytes(const b2ctr_cin_gemm_t* g) { return g ? b2ctr::cin_gemm_workspace_bytes(g) : 0; }
+b2ctr_status_t b2ctr_cin_gemm(const b2ctr_cin_gemm_t* g, void* workspace, size_t workspace_bytes, void* stream) {
+  return b2ctr::cin_gemm(g, workspace, workspace_bytes, (cudaStream_t)stream);
+}
+size_t b2ctr_att_gemm_workspace_bytes(const b2ctr_att_gemm_t* g) { return g ? b2ctr::att_gemm_workspace_bytes(g) : 0; }
+b2ctr_status_t b2ctr_att_gemm(const b2ctr_att_gemm_t* g, void* workspace, size_t workspace_bytes, void* stream) {
+  return b2ctr::att_gemm(g, workspace, workspace_bytes, (cudaStream_t)stream);
+}
+}

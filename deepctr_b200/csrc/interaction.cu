@@ -86,16 +86,40 @@ __global__ void __launch_bounds__(256)
     z[t] = x0.p[b * x0.sb + i * x0.si + dd * x0.sd] * xk.p[b * xk.sb + j * xk.si + dd * xk.sd];
   }
 }
+// T0[(b,d), i] = X0(b,i,d) (i < m), zero up to ld0: the per-row factor table of the generated outer product
+__global__ void __launch_bounds__(256)
+    cin_t0_kernel(CinView x0, float* t0, int64_t ld0, int64_t nb, int m, int d) {
+  const int64_t total = nb * d * ld0;
+  for (int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; t < total; t += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t row = t / ld0;
+    const int i = (int)(t - row * ld0);
+    const int64_t b = row / d;
+    const int dd = (int)(row - b * d);
+    t0[t] = i < m ? x0.p[b * x0.sb + i * x0.si + dd * x0.sd] : 0.f;
+  }
+}
+__global__ void __launch_bounds__(256)
+    cin_unpad_rows_kernel(const float* __restrict__ src, float* dst, int m, int h, int hp, int64_t n) {
+  const int64_t total = (int64_t)m * h * n;
+  for (int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; t < total; t += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t r = t / n;
+    const int64_t c = t - r * n;
+    const int i = (int)(r / h), j = (int)(r - (int64_t)i * h);
+    dst[t] = src[((int64_t)i * hp + j) * n + c];
+  }
+}
+
 // dX0(b,i,d) (+)= sum_j dZ[(b,d),(i,j)] * Xk(b,j,d) ;  dXk(b,j,d) (+)= sum_i dZ[(b,d),(i,j)] * X0(b,i,d)
 // one warp per (b,d) row: lanes stride j (coalesced reads of dZ), i walked sequentially.
 __global__ void __launch_bounds__(256)
     cin_outer_bwd_kernel(const float* __restrict__ dz, CinView x0, CinView xk, float* dx0, int64_t g0b,
                          int64_t g0i, int64_t g0d, int acc0, float* dxk, int64_t gkb, int64_t gki,
-                         int64_t gkd, int acck, int64_t nb, int m, int h, int d) {
+                         int64_t gkd, int acck, int64_t nb, int m, int h, int d, int hp) {
+  // dZ rows hold m groups of hp columns, of which the first h are used (hp = h: the dense layout)
   const int lane = threadIdx.x & 31;
   const int64_t nw = (int64_t)gridDim.x * (blockDim.x >> 5);
   const int64_t rows = nb * d;
-  const int64_t kdim = (int64_t)m * h;
+  const int64_t kdim = (int64_t)m * hp;
   for (int64_t row = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); row < rows; row += nw) {
     const int64_t b = row / d;
     const int dd = (int)(row - b * d);
@@ -105,7 +129,7 @@ __global__ void __launch_bounds__(256)
       const int j = j0 + lane;
       float a = 0.f;
       if (j < h)
-        for (int i = 0; i < m; ++i) a += g[i * h + j] * x0.p[b * x0.sb + i * x0.si + dd * x0.sd];
+        for (int i = 0; i < m; ++i) a += g[i * hp + j] * x0.p[b * x0.sb + i * x0.si + dd * x0.sd];
       if (j < h && dxk) {
         float* o = dxk + b * gkb + j * gki + dd * gkd;
         *o = acck ? *o + a : a;
@@ -115,7 +139,7 @@ __global__ void __launch_bounds__(256)
     if (dx0) {
       for (int i = 0; i < m; ++i) {
         float a = 0.f;
-        for (int j = lane; j < h; j += 32) a += g[i * h + j] * xk.p[b * xk.sb + j * xk.si + dd * xk.sd];
+        for (int j = lane; j < h; j += 32) a += g[i * hp + j] * xk.p[b * xk.sb + j * xk.si + dd * xk.sd];
         a = warp_sum(a);
         if (lane == 0) {
           float* o = dx0 + b * g0b + i * g0i + dd * g0d;
@@ -321,13 +345,33 @@ b2ctr_status_t b2ctr_cin_outer_bwd(const float* dz, const float* x0, int64_t s0b
                                    const float* xk, int64_t skb, int64_t ski, int64_t skd, float* dx0,
                                    int64_t g0b, int64_t g0i, int64_t g0d, int32_t acc0, float* dxk,
                                    int64_t gkb, int64_t gki, int64_t gkd, int32_t acck, int64_t nb, int32_t m,
-                                   int32_t h, int32_t d, void* stream) {
+                                   int32_t h, int32_t d, int32_t hp, void* stream) {
   B2_REQUIRE(dz && x0 && xk && (dx0 || dxk) && m > 0 && h > 0 && d > 0, "cin_outer_bwd: bad arguments");
+  if (hp <= 0) hp = h;
+  B2_REQUIRE(hp >= h, "cin_outer_bwd: hp < h");
   if (nb <= 0) return B2CTR_OK;
   CinView a{x0, s0b, s0i, s0d}, b{xk, skb, ski, skd};
   cin_outer_bwd_kernel<<<grid_for(nb * d, 8, 8), 256, 0, ST>>>(dz, a, b, dx0, g0b, g0i, g0d, acc0, dxk, gkb,
-                                                              gki, gkd, acck, nb, m, h, d);
+                                                              gki, gkd, acck, nb, m, h, d, hp);
   B2_CHECK_LAUNCH("b2ctr_cin_outer_bwd");
+  return B2CTR_OK;
+}
+
+b2ctr_status_t b2ctr_cin_t0(const float* x0, int64_t s0b, int64_t s0i, int64_t s0d, float* t0, int64_t ld0,
+                            int64_t nb, int32_t m, int32_t d, void* stream) {
+  B2_REQUIRE(x0 && t0 && m > 0 && d > 0 && ld0 >= m, "cin_t0: bad arguments");
+  if (nb <= 0) return B2CTR_OK;
+  CinView a{x0, s0b, s0i, s0d};
+  cin_t0_kernel<<<grid_for(nb * d * ld0, 256, 8), 256, 0, ST>>>(a, t0, ld0, nb, m, d);
+  B2_CHECK_LAUNCH("b2ctr_cin_t0");
+  return B2CTR_OK;
+}
+
+b2ctr_status_t b2ctr_cin_unpad_rows(const float* src, float* dst, int32_t m, int32_t h, int32_t hp, int64_t n,
+                                    void* stream) {
+  B2_REQUIRE(src && dst && m > 0 && h > 0 && hp >= h && n > 0, "cin_unpad_rows: bad arguments");
+  cin_unpad_rows_kernel<<<grid_for((int64_t)m * h * n, 256, 8), 256, 0, ST>>>(src, dst, m, h, hp, n);
+  B2_CHECK_LAUNCH("b2ctr_cin_unpad_rows");
   return B2CTR_OK;
 }
 

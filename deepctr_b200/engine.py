@@ -983,8 +983,8 @@ class Model(object):
             warnings.warn("metrics %r are not computed by this runtime (fit reports loss / val_loss only)" % (extra,))
         self.metrics = metrics or []
         self.metrics_names = ["loss"] + [m if isinstance(m, str) else m.__name__ for m in self.metrics]
-        if embedding_update not in ("auto", "dense", "sparse"):
-            raise ValueError("embedding_update must be auto / dense / sparse")
+        if embedding_update not in ("auto", "dense", "sparse", "sparse_deterministic"):
+            raise ValueError("embedding_update must be auto / dense / sparse / sparse_deterministic")
         self.planner.configure(self.optimizer, embedding_update)
         # CUDA-graph replay of the training step ('auto': on whenever the step is capturable)
         from . import ops as _ops
@@ -1164,9 +1164,11 @@ class Model(object):
             with torch.cuda.graph(graph, pool=self._graph_pool, capture_error_mode="thread_local"):
                 loss_sum, pred, batch = self._loss_step_impl(feed, labels, True)
         except Exception as exc:               # something on this model's path cannot be captured: stay eager
+            import traceback
             import warnings
-            warnings.warn("step graph capture failed (%s: %s); training continues with eager launches"
-                          % (type(exc).__name__, exc))
+            where = "".join(traceback.format_tb(exc.__traceback__)[-4:])
+            warnings.warn("step graph capture failed (%s: %s); training continues with eager launches\n%s"
+                          % (type(exc).__name__, exc, where))
             self.step_graph = "off"
             self.optimizer.iterations = it0
             for w in self.weights:             # nothing ran on the device; drop the half-built python state

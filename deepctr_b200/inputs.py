@@ -365,10 +365,21 @@ class EmbeddingPlanner(object):
     def configure(self, optimizer, mode):
         self.optimizer, self.mode = optimizer, mode
         total = sum(w.numel() for w in self.tables())
-        sparse = mode == "sparse" or (mode == "auto" and total > (1 << 22))
-        if sparse and optimizer.name != "sgd":
-            raise ValueError("embedding_update='sparse' (tables too large for dense updates) supports the "
-                             "'sgd' optimizer only; got %r" % optimizer.name)
+        sparse = mode in ("sparse", "sparse_deterministic") or (mode == "auto" and total > (1 << 22))
+        # 'sparse_deterministic': sort + ordered segmented reduce instead of fp32 atomics (bit-identical from run
+        # to run); it is also the path of row-state optimizers, i.e. Keras' lazy sparse Adagrad.  Keras' Adam
+        # decays m and v of EVERY row each step: it has no faithful row-wise form.
+        self.sorted_update = bool(sparse and (mode == "sparse_deterministic" or optimizer.name == "adagrad"))
+        if sparse and optimizer.name not in ("sgd", "adagrad"):
+            raise ValueError("row-wise (sparse) embedding updates support 'sgd' and 'adagrad'; %r keeps dense state "
+                             "for every row of every table - use embedding_update='dense' (O(vocabulary) per step)"
+                             % optimizer.name)
+        if self.sorted_update and not (self.fast and self._all_fast_single()):
+            if mode == "sparse_deterministic" or optimizer.name == "adagrad":
+                raise ValueError("the deterministic / Adagrad row-wise update covers models whose sparse features are "
+                                 "single-valued columns of one embedding_dim (the Criteo shape)")
+        if self.sorted_update and self.lin:
+            self.lin_hint = True        # the linear tables are updated by the same sorted pass from the first step on
         tabs = list(self.tables())
         for l in self.model.layers:          # unplanned Embedding layers follow the same policy
             if isinstance(l, Embedding) and all(l.embeddings is not w for w in tabs):
@@ -464,7 +475,7 @@ class EmbeddingPlanner(object):
             return self._arena
         import os
         self._arena = None
-        if os.environ.get("B2CTR_L2_PERSIST", "1") == "0" or getattr(self, "sharded", False):
+        if os.environ.get("B2CTR_L2_PERSIST", "0") != "1" or getattr(self, "sharded", False):
             return None
         ws, seen = [], set()
         for s_ in self.lin:
@@ -506,6 +517,9 @@ class EmbeddingPlanner(object):
                 break
         self.fast_n = n
         return n >= 1
+
+    def _all_fast_single(self):
+        return len(self.main) == self.fast_n and not self.seq and (not self.lin or self._lin_matches_fast())
 
     def _lin_matches_fast(self):
         """linear (dim-1) lookups mirror the fast features one-to-one -> summed inside the kernel."""
@@ -735,12 +749,34 @@ class EmbeddingPlanner(object):
                     lin_scale = max(abs(sc) for _, sc in lt) * (-1.0 if any(sc < 0 for _, sc in lt) else 1.0)
                 bplan = K.UniformPlan(feats, lin_tabs, None, main.data, None, None, plan.g.fm_mask[0])
                 bplan.g.x_cols = plan.g.x_cols
+                if getattr(self, "sorted_update", False) and all(sc < 0 for _, sc in tgts):
+                    o = opt["optimizer"]
+                    adagrad = o.name == "adagrad"
+                    acc = lacc = None
+                    if adagrad:
+                        acc = [self._adagrad_state(s.emb.embeddings) for s in fast_slots]
+                        lacc = [self._adagrad_state(s.emb.embeddings).reshape(-1) for s in self.lin] if lin_fused else None
+                    K.embed_update_sorted(bplan, dx, None if dfm is None else dfm.reshape(-1).contiguous(),
+                                          None if dlin is None else dlin.reshape(-1).contiguous(),
+                                          1 if adagrad else 0, o.lr, o.lr, 1e-7, acc, lacc, batch)
+                    return self._backward_generic(feed, bufs, generic, opt, batch)
                 arena = getattr(self, "_arena", None)
                 if arena and lin_tabs is not None and all(sc < 0 for _, sc in lt):
                     bplan.set_window(arena[1])        # fused SGD on the linear tables inside the arena
                 K.embed_scatter_uniform_bwd(bplan, dx, None if dfm is None else dfm.reshape(-1).contiguous(),
                                             None if dlin is None else dlin.reshape(-1).contiguous(),
                                             scale, lin_scale, batch)
+        self._backward_generic(feed, bufs, generic, opt, batch)
+
+    @staticmethod
+    def _adagrad_state(w):
+        acc = w.opt_state.get("acc")
+        if acc is None:
+            acc = w.opt_state["acc"] = torch.empty_like(w.data)
+            K.fill(acc, 0.1)               # Keras initial_accumulator_value
+        return acc
+
+    def _backward_generic(self, feed, bufs, generic, opt, batch):
         feats, scales = [], []
         for s in generic:
             if not s.emb.embeddings.trainable:
@@ -924,7 +960,7 @@ class Feeder(object):
             nbytes[i] = b * w * isz
             offs[i] = off * isz
             off += b * w
-        L.check(L.lib().b2ctr_host_pack(src, nbytes, offs, n, C.c_void_p(sn.ctypes.data), 0), "host_pack")
+        L.check(L.lib().b2ctr_host_pack(src, nbytes, offs, n, C.c_void_p(sn.ctypes.data), _pack_threads()), "host_pack")
 
     def _upload(self, host, dev):
         dev.copy_(host, non_blocking=True)
@@ -1063,6 +1099,24 @@ class Feeder(object):
         stage, dbuf = self._stage("labels", (a.shape[0],), torch.float32)
         stage.numpy()[:] = a
         return self._upload(stage, dbuf)
+
+
+_PACK_THREADS = None
+
+
+def _pack_threads():
+    """Size of the native staging pool: the cores THIS process may use (its affinity mask, shared between the
+    ranks of the node under torchrun), leaving room for the Python threads; between 1 and 8."""
+    global _PACK_THREADS
+    if _PACK_THREADS is None:
+        import os
+        try:
+            avail = len(os.sched_getaffinity(0))
+        except AttributeError:
+            avail = os.cpu_count() or 1
+        local = max(1, int(os.environ.get("LOCAL_WORLD_SIZE", "1")))
+        _PACK_THREADS = max(1, min(8, (avail // local - 2) // 2))
+    return _PACK_THREADS
 
 
 def _dense_strides(shape):

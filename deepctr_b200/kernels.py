@@ -177,6 +177,21 @@ def embed_scatter_uniform_bwd(plan, dx, dfm, dlinear, scale, lin_scale, batch):
             "embed_scatter_uniform_bwd")
 
 
+def embed_update_sorted(plan, dx, dfm, dlinear, optimizer, lr, lin_lr, eps, acc_tables, lin_acc_tables, batch):
+    """Deterministic fused update (sort by (feature, id) + ordered segmented reduce, one write per row):
+    optimizer 0 = SGD, 1 = Keras Adagrad (lazy / sparse apply) with per-element accumulators."""
+    nf = plan.g.nfeat
+    dim = plan.feat_arr[0].dim
+    nbytes = L.lib().b2ctr_embed_update_sorted_workspace_bytes(nf, dim, batch)
+    dev = dx.device if dx is not None else (dfm.device if dfm is not None else dlinear.device)
+    ws = workspace(nbytes, dev)
+    acc = (C.c_void_p * nf)(*[t.data_ptr() for t in acc_tables]) if acc_tables is not None else None
+    lacc = (C.c_void_p * nf)(*[t.data_ptr() for t in lin_acc_tables]) if lin_acc_tables is not None else None
+    L.check(L.lib().b2ctr_embed_update_sorted(C.byref(plan.g), ptr(dx), ptr(dfm), ptr(dlinear), optimizer, lr, lin_lr,
+                                              eps, acc, lacc, batch, ptr(ws), nbytes, stream()),
+            "embed_update_sorted")
+
+
 def hash64(ids, num_buckets, mask_zero):
     _require_cuda(ids)
     ids = ids.contiguous()
@@ -450,7 +465,7 @@ def profile_summary():
     return out
 
 
-for _n in ("split_planes", "embed_gather_fwd", "embed_scatter_add", "embed_gather_uniform_fwd", "embed_scatter_uniform_bwd",
+for _n in ("embed_update_sorted", "split_planes", "embed_gather_fwd", "embed_scatter_add", "embed_gather_uniform_fwd", "embed_scatter_uniform_bwd",
            "hash64", "gemm", "bias_act_bwd", "act_fwd", "add_n", "axpy", "fill", "copy2d", "rowsum", "fm_fwd",
            "fm_bwd", "predict_loss", "sgd_step", "adam_step", "adagrad_step", "mask_nonzero_and",
            "mask_from_len"):
@@ -496,11 +511,69 @@ def cin_outer_fwd(x0, v0, xk, vk, z, b0, nb, m, h, d):
               vk[2], ptr(z), nb, m, h, d, stream())
 
 
-def cin_outer_bwd(dz, x0, v0, xk, vk, dx0, g0, acc0, dxk, gk, acck, b0, nb, m, h, d):
+def cin_outer_bwd(dz, x0, v0, xk, vk, dx0, g0, acc0, dxk, gk, acck, b0, nb, m, h, d, hp=0):
     _lib_call("cin_outer_bwd", ptr(dz), _off(x0, b0 * v0[0]), v0[0], v0[1], v0[2], _off(xk, b0 * vk[0]), vk[0],
               vk[1], vk[2], _off(dx0, b0 * g0[0]) if dx0 is not None else C.c_void_p(0), g0[0], g0[1], g0[2],
               int(acc0), _off(dxk, b0 * gk[0]) if dxk is not None else C.c_void_p(0), gk[0], gk[1], gk[2],
-              int(acck), nb, m, h, d, stream())
+              int(acck), nb, m, h, d, hp, stream())
+
+
+def cin_t0(x0, v0, nb, m, d, ld0):
+    """T0[(b,d), i] = X0(b,i,d), zero-padded to ld0 columns: the per-row factors of the generated outer product."""
+    t0 = torch.empty((nb * d, ld0), dtype=torch.float32, device=x0.device)
+    _lib_call("cin_t0", ptr(x0), v0[0], v0[1], v0[2], ptr(t0), ld0, nb, m, d, stream())
+    return t0
+
+
+def cin_filter_planes(w2d, m, h, hp):
+    """bf16 hi/lo planes of the filter in the padded layout W'[i*hp + j, n] (w2d: [m*h, n])."""
+    n = w2d.shape[1]
+    planes = torch.empty((L.lib().b2ctr_cin_filter_planes_bytes(m, hp, n),), dtype=torch.uint8, device=w2d.device)
+    _lib_call("cin_filter_planes", ptr(w2d), m, h, hp, n, ptr(planes), stream())
+    return planes
+
+
+def cin_gemm(mode, t0, xk, ldk, rows, m, h, hp, n, planes, bias=None, act=L.ACT_NONE, split_k=1, out=None):
+    """mode 0: Y[rows, n] = act(Z W' + bias) with planes = cin_filter_planes; mode 1: dW'[m*hp, n] = Z^T dY with
+    planes = split_planes(dY).  Z[r, i*hp+j] = t0[r,i] * xk[r,j] is generated inside the GEMM producer."""
+    g = L.CinGemm()
+    g.t0, g.ld0, g.xk, g.ldk, g.rows = t0.data_ptr(), t0.stride(0), xk.data_ptr(), ldk, rows
+    g.m, g.h, g.hp, g.n = m, h, hp, n
+    g.w_planes = planes.data_ptr() if mode == 0 else None
+    g.dy_planes = planes.data_ptr() if mode == 1 else None
+    if out is None:
+        out = torch.empty((rows if mode == 0 else m * hp, n), dtype=torch.float32, device=t0.device)
+    g.c, g.ldc = out.data_ptr(), out.stride(0)
+    g.bias = bias.data_ptr() if bias is not None else None
+    g.act, g.mode, g.split_k = act, mode, split_k
+    nbytes = L.lib().b2ctr_cin_gemm_workspace_bytes(C.byref(g))
+    ws = workspace(nbytes, t0.device)
+    L.check(L.lib().b2ctr_cin_gemm(C.byref(g), ptr(ws), nbytes, stream()), "cin_gemm")
+    return out
+
+
+def att_gemm(mode, q2d, ldq, keys2d, key_batch_stride, batch, T, E, n, planes, bias=None, act=L.ACT_NONE, split_k=1):
+    """First LocalActivationUnit layer with its [q, k, q-k, q*k] input generated inside the GEMM producer.
+    mode 0: [B*T, n] = act(A W + bias) (planes of W [4E, n]); mode 1: [4E, n] = A^T dY (planes of dY [B*T, n])."""
+    g = L.AttGemm()
+    g.query, g.ldq, g.keys, g.key_batch_stride = q2d.data_ptr(), ldq, keys2d.data_ptr(), key_batch_stride
+    g.batch, g.maxlen, g.dim, g.n = batch, T, E, n
+    g.planes = planes.data_ptr()
+    out = torch.empty((batch * T if mode == 0 else 4 * E, n), dtype=torch.float32, device=q2d.device)
+    g.c, g.ldc = out.data_ptr(), n
+    g.bias = bias.data_ptr() if bias is not None else None
+    g.act, g.mode, g.split_k = act, mode, split_k
+    nbytes = L.lib().b2ctr_att_gemm_workspace_bytes(C.byref(g))
+    ws = workspace(nbytes, q2d.device)
+    L.check(L.lib().b2ctr_att_gemm(C.byref(g), ptr(ws), nbytes, stream()), "att_gemm")
+    return out
+
+
+def cin_unpad_rows(src, m, h, hp):
+    n = src.shape[1]
+    dst = torch.empty((m * h, n), dtype=torch.float32, device=src.device)
+    _lib_call("cin_unpad_rows", ptr(src), ptr(dst), m, h, hp, n, stream())
+    return dst
 
 
 def cin_sum_d(y, ldy, col0, ncols, d, out, ldo, out_col, b0, nb):
@@ -632,7 +705,8 @@ def dropout(x, rate, seed):
     return y
 
 
-for _n in ("ewise", "cross_vector_fwd", "cross_vector_bwd", "cin_outer_fwd", "cin_outer_bwd", "cin_sum_d",
+for _n in ("ewise", "cross_vector_fwd", "cross_vector_bwd", "cin_t0", "cin_filter_planes", "cin_gemm", "cin_unpad_rows", "att_gemm",
+           "cin_outer_fwd", "cin_outer_bwd", "cin_sum_d",
            "cin_expand_grad", "interacting_fwd", "interacting_bwd", "din_att_input_fwd", "din_att_input_bwd",
            "din_pool_fwd", "din_pool_bwd", "seqpool_fwd", "seqpool_bwd", "seqweight", "seqscale", "colstats",
            "bn_apply", "bn_bwd", "dice_fwd", "dice_bwd", "dropout"):
@@ -683,7 +757,8 @@ for _n in ("shard_bucketize", "shard_fill", "shard_gather_rows", "shard_scatter_
     globals()[_n] = _timed(globals()[_n])
 
 
-for _n in ("ewise", "cross_vector_fwd", "cross_vector_bwd", "cin_outer_fwd", "cin_outer_bwd", "cin_sum_d",
+for _n in ("ewise", "cross_vector_fwd", "cross_vector_bwd", "cin_t0", "cin_filter_planes", "cin_gemm", "cin_unpad_rows", "att_gemm",
+           "cin_outer_fwd", "cin_outer_bwd", "cin_sum_d",
            "cin_expand_grad", "interacting_fwd", "interacting_bwd", "din_att_input_fwd", "din_att_input_bwd",
            "din_pool_fwd", "din_pool_bwd", "seqpool_fwd", "seqpool_bwd", "seqweight", "seqscale", "colstats",
            "moving_update", "bn_apply", "bn_bwd", "dice_fwd", "dice_bwd", "dropout"):

@@ -57,14 +57,18 @@ class DNN(Layer):
                 self.activation_layers[i]._maybe_build(shape)
         self.built = True
 
-    def call(self, inputs, training=None, **kwargs):
+    def call(self, inputs, training=None, first=None, **kwargs):
+        """``first(kernel, bias, activation)``: an alternative implementation of layer 0's  act(x W + b)  for a
+        caller that never materialises x (the DIN attention unit generates it inside the GEMM)."""
         deep_input = inputs
         for i in range(len(self.hidden_units)):
             act_layer = self.activation_layers[i]
+            dense = first if (i == 0 and first is not None) else \
+                (lambda k, b, a, x=deep_input: ops.dense(x, k, b, a))
             if act_layer is None:
-                fc = ops.dense(deep_input, self.kernels[i], self.bias[i], self.act_names[i])
+                fc = dense(self.kernels[i], self.bias[i], self.act_names[i])
             else:
-                fc = ops.dense(deep_input, self.kernels[i], self.bias[i], None)
+                fc = dense(self.kernels[i], self.bias[i], None)
                 if self.use_bn:
                     self.bn_layers[i]._maybe_build(fc.shape)
                     fc = self.bn_layers[i].call(fc, training=training)
@@ -159,8 +163,13 @@ class LocalActivationUnit(Layer):
 
     def call(self, inputs, training=None, **kwargs):
         query, keys = inputs
-        att_input = ops.din_att_input(query, keys)                       # [B,T,4E]   core.py:98-101
-        att_out = self.dnn.call(att_input, training=training)            # core.py:103
+        if len(self.hidden_units) > 0 and ops.din_att_fusable(query, keys, int(self.hidden_units[0])):
+            # [q, k, q-k, q*k] is generated inside the first GEMM's producer: the [B,T,4E] tensor never exists
+            att_out = self.dnn.call(None, training=training,
+                                    first=lambda k, b, a: ops.din_att_first(query, keys, k, b, a))
+        else:
+            att_input = ops.din_att_input(query, keys)                   # [B,T,4E]   core.py:98-101
+            att_out = self.dnn.call(att_input, training=training)        # core.py:103
         return ops.dense(att_out, self.kernel, self.bias, None)          # [B,T,1]    core.py:106
 
     def compute_output_shape(self, input_shape):

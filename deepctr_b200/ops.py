@@ -493,9 +493,109 @@ def cross_matrix(x0, xl, w, bias):
 CIN_CHUNK_BYTES = 48 << 20      # outer-product chunk kept well inside the 126 MB L2
 
 
+CIN_FUSED = True              # generate the outer product inside the tcgen05 GEMM producer (b2ctr_cin_gemm)
+CIN_DZ_CHUNK_BYTES = 512 << 20
+
+
 def cin(x, filters, biases, layer_size, activation, split_half):
+    B, m, D = x.shape
     with K.profile_tag("cin"):
+        hid = [n // 2 if split_half else n for n in layer_size[:-1]]
+        if (CIN_FUSED and GEMM_PRECISION == L.GEMM_BF16X3 and B * D >= 256 and D in (4, 8, 16, 32, 64, 128)
+                and min(layer_size) >= 8 and all(n % 4 == 0 for n in layer_size) and all(h % 4 == 0 for h in hid)):
+            return _cin_fused(x, filters, biases, layer_size, activation, split_half)
         return _cin(x, filters, biases, layer_size, activation, split_half)
+
+
+def _cin_pad(h):
+    return 32 if h <= 32 else (h + 63) // 64 * 64
+
+
+def _cin_fused(x, filters, biases, layer_size, activation, split_half):
+    """CIN (layers/interaction.py:277-325) with the outer product Z[(b,d), (i,j)] = X0(b,i,d) X_k(b,j,d) GENERATED
+    by the producer warps of the tensor-core GEMM instead of being written anywhere: forward Y = act(Z W + b) and
+    the filter gradient dW = Z^T dY both read only the two factors (T0 = X0 transposed to [(b,d), m], X_k as the
+    previous layer's [(b,d), N] activations).  Only dZ = dY W^T of the backward pass exists in memory, in row chunks."""
+    B, m, D = x.shape
+    x2, ldx = x.flat2d()
+    if x2 is None:
+        x2 = E.contiguous(x).reshape(B, m * D)
+        ldx = m * D
+    act = L.ACT_BY_NAME[activation]
+    nl = len(layer_size)
+    hs = [m] + [size // 2 if split_half else size for size in layer_size]
+    direct = [((size // 2, size // 2) if (split_half and i != nl - 1) else (0, size)) for i, size in enumerate(layer_size)]
+    out_cols = sum(nc for _, nc in direct)
+    out = _empty((B, out_cols), x2)
+    rows = B * D
+    v0 = (ldx, D, 1)
+    ld0 = 32 if m <= 32 else (m + 63) // 64 * 64
+    t0 = K.cin_t0(x2, v0, B, m, D, ld0)                       # [rows, ld0]
+    tv0 = (D * ld0, 1, ld0)                                   # T0 seen as X0(b,i,d)
+    ws2d = [_wdata(f).reshape(-1, f.shape[-1]) for f in filters]
+    bs = [_wdata(bv) for bv in biases]
+    hps = [_cin_pad(hs[i]) for i in range(nl)]
+    wplanes, ys = [], []
+    oc = 0
+    for i, size in enumerate(layer_size):
+        h, hp = hs[i], hps[i]
+        xk, ldk = (t0, ld0) if i == 0 else (ys[-1], layer_size[i - 1])
+        wp = K.cin_filter_planes(ws2d[i], m, h, hp)
+        y = K.cin_gemm(0, t0, xk, ldk, rows, m, h, hp, size, wp, bias=bs[i], act=act)
+        K.cin_sum_d(y, size, direct[i][0], direct[i][1], D, out, out_cols, oc, 0, B)
+        oc += direct[i][1]
+        wplanes.append(wp)
+        ys.append(y)
+    res = E.Var(out)
+
+    def bwd(grads):
+        g = grads[0]
+        if not g.is_contiguous():
+            g = g.contiguous()
+        dx = _empty((B, m * D), x2)
+        K.fill(dx, 0.0)
+        gx = (m * D, D, 1)
+        dh = None
+        col = out_cols
+        for i in range(nl - 1, -1, -1):
+            size, h, hp = layer_size[i], hs[i], hps[i]
+            kq = m * hp
+            col -= direct[i][1]
+            dy = _empty((rows, size), x2)
+            K.cin_expand_grad(g, out_cols, col, direct[i][0], direct[i][1], dh, hs[i + 1] if dh is not None else 0,
+                              hs[i + 1] if dh is not None else 0, dy, size, D, 0, B)
+            if act != L.ACT_NONE and K.planes_fusable(rows, size):
+                dz_, db, dzp = K.bias_act_bwd(dy, ys[i], act, want_dz=True, want_dbias=True, want_planes=True)
+            else:
+                dz_, db = K.bias_act_bwd(dy, ys[i], act, want_dz=act != L.ACT_NONE, want_dbias=True)
+                if dz_ is None:
+                    dz_ = dy
+                dzp = K.split_planes(dz_)
+            E.add_grad(biases[i], db)
+            xk, ldk = (t0, ld0) if i == 0 else (ys[i - 1], layer_size[i - 1])
+            xkv = tv0 if i == 0 else (D * layer_size[i - 1], 1, layer_size[i - 1])
+            if filters[i].requires_grad:
+                dwp = K.cin_gemm(1, t0, xk, ldk, rows, m, h, hp, size, dzp, split_k=_split_k(kq, size, rows))
+                E.add_grad(filters[i], K.cin_unpad_rows(dwp, m, h, hp).reshape(filters[i].shape))
+            # dZ = dY W'^T in row chunks, folded back onto the two factors
+            dhid = _empty((rows, h), x2) if i > 0 else None
+            chunk = max(256, min(rows, CIN_DZ_CHUNK_BYTES // (4 * kq)) // 256 * 256)
+            dzf = _empty((min(chunk, rows), kq), x2)
+            for r0 in range(0, rows, chunk):
+                nr = min(chunk, rows - r0)
+                K.gemm(dz_[r0:r0 + nr], dz_, c=dzf[:nr], trans_b=True, precision=L.GEMM_BF16X3, m=nr, n=kq, k=size,
+                       b_planes=wplanes[i])
+                b0, nbk = r0 // D, nr // D
+                if i == 0:
+                    K.cin_outer_bwd(dzf, t0, tv0, t0, tv0, dx, gx, True, dx, gx, True, b0, nbk, m, h, D, hp)
+                else:
+                    K.cin_outer_bwd(dzf, t0, tv0, ys[i - 1], xkv, dx, gx, True, dhid, (D * h, 1, h), False, b0, nbk,
+                                    m, h, D, hp)
+            dh = dhid
+        E.add_grad(x, dx.reshape(x.shape))
+
+    E.record([res], [x] + list(filters) + list(biases), bwd)
+    return res
 
 
 def _cin(x, filters, biases, layer_size, activation, split_half):
@@ -646,6 +746,68 @@ def din_att_input(query, keys):
 
     E.record([res], [query, keys], bwd)
     return res
+
+
+DIN_FUSED = True     # generate [q, k, q-k, q*k] inside the first attention GEMM (b2ctr_att_gemm)
+
+
+def din_att_fusable(query, keys, n_out):
+    B, T, Edim = keys.shape
+    return (DIN_FUSED and GEMM_PRECISION == L.GEMM_BF16X3 and Edim % 8 == 0 and B * T >= 256 and n_out >= 8
+            and n_out % 4 == 0)
+
+
+def din_att_first(query, keys, w, b, activation):
+    """act([q, k, q-k, q*k] @ w + b) -> [B, T, n] without materialising the [B, T, 4E] attention input
+    (layers/core.py:96-103).  The backward pass generates the same operand again for the kernel gradient; only
+    d(input) = dZ W^T exists in memory, to be folded back onto q and k."""
+    B, T, Edim = keys.shape
+    qt, ldq = query.flat2d()
+    if qt is None or ldq % 4 or qt.data_ptr() % 16:
+        qt = E.contiguous(query).reshape(B, Edim)
+        ldq = Edim
+    kt, ldk = keys.flat2d()
+    if kt is None or ldk % 4 or kt.data_ptr() % 16:
+        kt = E.contiguous(keys).reshape(B, T * Edim)
+        ldk = T * Edim
+    act = L.ACT_BY_NAME[activation]
+    wd, bd = _wdata(w), (_wdata(b) if b is not None else None)
+    n = wd.shape[1]
+    wp = K.split_planes(wd)
+    y = K.att_gemm(0, qt, ldq, kt, ldk, B, T, Edim, n, wp, bias=bd, act=act)
+    out = E.Var(y.reshape(B, T, n))
+    rows = B * T
+
+    def bwd(grads):
+        dy = grads[0].reshape(rows, n)
+        if not dy.is_contiguous():
+            dy = dy.contiguous()
+        need_db = b is not None and b.requires_grad
+        dzp = None
+        if act != L.ACT_NONE or need_db:
+            if act != L.ACT_NONE and K.planes_fusable(rows, n):
+                dz, db, dzp = K.bias_act_bwd(dy, y, act, want_dz=True, want_dbias=need_db, want_planes=True)
+            else:
+                dz, db = K.bias_act_bwd(dy, y, act, want_dz=act != L.ACT_NONE, want_dbias=need_db)
+            if dz is None:
+                dz = dy
+        else:
+            dz, db = dy, None
+        if dzp is None:
+            dzp = K.split_planes(dz)
+        if w.requires_grad:
+            dw = K.att_gemm(1, qt, ldq, kt, ldk, B, T, Edim, n, dzp, split_k=_split_k(4 * Edim, n, rows))
+            E.add_grad(w, dw)
+        if need_db:
+            E.add_grad(b, db)
+        if query.requires_grad or keys.requires_grad:
+            da = K.gemm(dz, wd, trans_b=True, precision=L.GEMM_BF16X3, m=rows, n=4 * Edim, k=n, a_planes=dzp, b_planes=wp)
+            dq, dk = K.din_att_input_bwd(qt, ldq, kt, ldk, da, B, T, Edim)
+            E.add_grad(query, dq.reshape(query.shape))
+            E.add_grad(keys, dk.reshape(keys.shape))
+
+    E.record([out], [query, keys, w, b], bwd)
+    return out
 
 
 def din_attention_pool(score, keys, mask_u8, weight_normalization, return_score):

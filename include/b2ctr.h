@@ -197,6 +197,21 @@ B2CTR_API b2ctr_status_t b2ctr_embed_scatter_uniform_bwd(const b2ctr_uniform_gat
  * ValueError like TF-CPU when it is non-zero. */
 B2CTR_API b2ctr_status_t b2ctr_embed_oob_count(int64_t* count, int32_t reset, void* stream);
 
+/* DETERMINISTIC fused update of the Criteo-shaped fast path (same descriptor and gradients as
+ * b2ctr_embed_scatter_uniform_bwd; tables whole, world <= 1): the lookups are sorted by (feature, id), the
+ * gradient rows of duplicate ids are summed in ascending sample order in fp32 and every touched row is written
+ * ONCE - bit-identical from run to run, and the home of row-state optimizers:
+ *   optimizer 0: w -= lr * g                       (row-wise SGD)
+ *   optimizer 1: acc += g^2; w -= lr * g / (sqrt(acc) + eps)   (Keras Adagrad, whose sparse apply is lazy)
+ * acc_tables / lin_acc_tables: host arrays [nfeat] of device pointers shaped like the tables (optimizer 1).
+ * Uses cub::DeviceRadixSort from the CUDA toolkit for the key sort. */
+B2CTR_API size_t b2ctr_embed_update_sorted_workspace_bytes(int32_t nfeat, int32_t dim, int64_t batch);
+B2CTR_API b2ctr_status_t b2ctr_embed_update_sorted(const b2ctr_uniform_gather_t* g, const float* dx,
+                                                  const float* dfm, const float* dlinear, int32_t optimizer,
+                                                  float lr, float lin_lr, float eps, float* const* acc_tables,
+                                                  float* const* lin_acc_tables, int64_t batch, void* workspace,
+                                                  size_t workspace_bytes, void* stream);
+
 /* Hash (deepctr/layers/utils.py:89-112): ids -> int64 buckets, FarmHash Fingerprint64 of the
  * decimal ASCII form.  mask_zero: 0 stays 0, others land in [1, num_buckets).               */
 B2CTR_API b2ctr_status_t b2ctr_hash64(const void* ids, int32_t idx_dtype, int64_t n,
@@ -358,8 +373,57 @@ B2CTR_API b2ctr_status_t b2ctr_cin_outer_bwd(const float* dz, const float* x0, i
                                             int64_t skd, float* dx0, int64_t g0b, int64_t g0i,
                                             int64_t g0d, int32_t acc0, float* dxk, int64_t gkb,
                                             int64_t gki, int64_t gkd, int32_t acck, int64_t nb,
-                                            int32_t m, int32_t h, int32_t d, void* stream);
+                                            int32_t m, int32_t h, int32_t d, int32_t hp, void* stream);
+/* (hp: dZ rows hold m groups of hp columns of which the first h are used - the padded layout of
+ *  b2ctr_cin_gemm; 0 or h = dense) */
 /* out[b, out_col+n] = sum_d y[(b,d), col0+n]  (reduce_sum over D of the direct maps, :322-323) */
+/* CIN filter contraction with the outer product GENERATED inside the GEMM producer (never stored):
+ *   Z[r, i*hp + j] = t0[r, i] * xk[r, j]     r = b*D + d;  t0[r, i] = X0(b,i,d);  xk[r, j] = X_k(b,j,d), j < h
+ * hp = h padded to 32 (h <= 32) or to a multiple of 64, so that a 64-deep k-block never straddles an i; the
+ * filter is used in the matching padded layout W'[i*hp + j, n] (b2ctr_cin_filter_planes: bf16 hi/lo planes).
+ *   mode 0:  c[rows, n]   = act(Z W' + bias)     (forward; deepctr/layers/interaction.py:291-306)
+ *   mode 1:  c[m*hp, n]   = Z^T dY               (filter gradient; dY given as b2ctr_split_planes of [rows, n])
+ * tcgen05 split-bf16 (BF16X3) arithmetic, TMA for the B operand, 128 producer threads generate A. */
+typedef struct b2ctr_cin_gemm {
+  const float* t0; int64_t ld0;      /* [rows, ld0], columns >= m are ignored                          */
+  const float* xk; int64_t ldk;      /* [rows, ldk], 16-byte aligned rows (ldk % 4 == 0)                */
+  int64_t rows;
+  int32_t m, h, hp, n;
+  const void* w_planes;              /* mode 0                                                         */
+  const void* dy_planes;             /* mode 1                                                         */
+  float* c; int64_t ldc;
+  const float* bias;                 /* mode 0: [n] or NULL                                            */
+  int32_t act, mode, split_k;
+} b2ctr_cin_gemm_t;
+B2CTR_API size_t b2ctr_cin_filter_planes_bytes(int32_t m, int32_t hp, int64_t n);
+B2CTR_API b2ctr_status_t b2ctr_cin_filter_planes(const float* w, int32_t m, int32_t h, int32_t hp, int64_t n,
+                                                void* planes, void* stream);
+B2CTR_API size_t b2ctr_cin_gemm_workspace_bytes(const b2ctr_cin_gemm_t* g);
+B2CTR_API b2ctr_status_t b2ctr_cin_gemm(const b2ctr_cin_gemm_t* g, void* workspace, size_t workspace_bytes,
+                                       void* stream);
+/* First layer of DIN's LocalActivationUnit (deepctr/layers/core.py:96-103) with its input
+ *   A[(b,t), :] = [ q_b , k_bt , q_b - k_bt , q_b * k_bt ]     ([B*T, 4E]; the reference materialises it)
+ * GENERATED inside the GEMM producer from the queries [B, E] and the keys [B, T, E]:
+ *   mode 0:  c[B*T, n] = act(A W + bias), planes = b2ctr_split_planes of W [4E, n]
+ *   mode 1:  c[4E, n]  = A^T dY,          planes = b2ctr_split_planes of dY [B*T, n]     (kernel gradient)  */
+typedef struct b2ctr_att_gemm {
+  const float* query; int64_t ldq;              /* [batch, ldq], first `dim` columns                         */
+  const float* keys; int64_t key_batch_stride;  /* keys of sample b start at keys + b*key_batch_stride, rows of `dim` */
+  int64_t batch; int32_t maxlen, dim, n;
+  const void* planes;
+  float* c; int64_t ldc;
+  const float* bias; int32_t act, mode, split_k;
+} b2ctr_att_gemm_t;
+B2CTR_API size_t b2ctr_att_gemm_workspace_bytes(const b2ctr_att_gemm_t* g);
+B2CTR_API b2ctr_status_t b2ctr_att_gemm(const b2ctr_att_gemm_t* g, void* workspace, size_t workspace_bytes,
+                                       void* stream);
+/* t0[(b*D + d), i] = X0(b,i,d) for i < m, zero for m <= i < ld0 (X0 given by its three strides). */
+B2CTR_API b2ctr_status_t b2ctr_cin_t0(const float* x0, int64_t s0b, int64_t s0i, int64_t s0d, float* t0,
+                                     int64_t ld0, int64_t nb, int32_t m, int32_t d, void* stream);
+/* dst[i*h + j, :] = src[i*hp + j, :] (j < h): the gradient of the padded filter back in W's layout. */
+B2CTR_API b2ctr_status_t b2ctr_cin_unpad_rows(const float* src, float* dst, int32_t m, int32_t h, int32_t hp,
+                                             int64_t n, void* stream);
+
 B2CTR_API b2ctr_status_t b2ctr_cin_sum_d(const float* y, int64_t ldy, int32_t col0, int32_t ncols,
                                         int32_t d, float* out, int64_t ldo, int32_t out_col,
                                         int64_t nb, void* stream);

@@ -375,3 +375,88 @@ def test_dropout_mask_is_consistent_between_forward_and_backward(cuda):
     a = layer(np.ones((10, 4), np.float32)).data.cpu().numpy()
     b = layer(np.ones((10, 4), np.float32)).data.cpu().numpy()
     assert np.array_equal(a, b)
+
+
+@pytest.mark.parametrize("B,F,E_,layer_size,split_half,act", [
+    (64, 6, 8, (40, 24), True, "relu"),          # h = 6 -> hp 32, h = 20 -> hp 32
+    (64, 6, 8, (40, 24), False, "linear"),       # h = 40 -> hp 64
+    (24, 5, 16, (136, 16), True, "relu"),        # h = 68 -> hp 128 (two k-blocks per i), N = 136 -> two N tiles? (bn 256)
+    (300, 26, 16, (128, 128), True, "relu"),     # the C3 layer sizes: K' = 832 / 1664, 2-CTA tiles, ragged last row tile
+])
+def test_cin_generated_outer_product(cuda, B, F, E_, layer_size, split_half, act):
+    """b2ctr_cin_gemm: the outer product is generated inside the tensor-core GEMM producer (forward and filter
+    gradient); checked against the oracle's literal op sequence, all gradients."""
+    from deepctr_b200.layers import CIN
+    from deepctr_b200 import ops, _lib as L
+    ops.set_gemm_precision("bf16x3")
+    assert ops.CIN_FUSED
+    rng = np.random.RandomState(21)
+    x = rng.normal(0, 0.5, size=(B, F, E_)).astype(np.float32)
+    layer = CIN(layer_size, act, split_half, seed=3)
+    layer.build((None, F, E_))
+    for w in layer.weights:
+        w.set_value(rng.normal(0, 0.2, size=w.shape).astype(np.float32))
+    L.reset_launch_count()
+    old = ops.CIN_DZ_CHUNK_BYTES
+    ops.CIN_DZ_CHUNK_BYTES = 4 * 832 * 1024          # several dZ row chunks at the larger shapes
+    try:
+        out, gy, gin, gw = _run(layer, x, rng)
+    finally:
+        ops.CIN_DZ_CHUNK_BYTES = old
+    xt = _t(x)
+    fs = [_t(w.value()) for w in layer.filters]
+    bs = [_t(w.value()) for w in layer.bias]
+    want = O.cin(xt, fs, bs, layer_size, act, split_half)
+    (want * _t(gy, False)).sum().backward()
+
+    def close(a, b, what):
+        b = b.detach().numpy() if hasattr(b, "detach") else np.asarray(b)
+        a = np.asarray(a)
+        np.testing.assert_allclose(a.reshape(b.shape), b, rtol=2e-4, atol=2e-4 * float(np.abs(b).max()), err_msg=what)
+    close(out, want, "out")
+    close(gin[0], xt.grad, "dx")
+    for i in range(len(layer_size)):
+        close(gw["filter%d" % i], fs[i].grad, "filter%d" % i)
+        close(gw["bias%d" % i], bs[i].grad, "bias%d" % i)
+
+
+@pytest.mark.parametrize("B,T,E_,n,act", [(16, 20, 16, 24, "sigmoid"), (40, 50, 64, 80, "relu"), (9, 31, 8, 36, None)])
+def test_din_first_attention_layer_generated_input(cuda, B, T, E_, n, act):
+    """b2ctr_att_gemm: act([q, k, q-k, q*k] W + b) with the [B,T,4E] input generated inside the GEMM producer,
+    forward + every gradient against torch."""
+    from deepctr_b200 import engine as E, ops
+    ops.set_gemm_precision("bf16x3")
+    rng = np.random.RandomState(23)
+    q = rng.normal(0, 0.5, size=(B, 1, E_)).astype(np.float32)
+    k = rng.normal(0, 0.5, size=(B, T, E_)).astype(np.float32)
+    w = rng.normal(0, 0.2, size=(4 * E_, n)).astype(np.float32)
+    b = rng.normal(0, 0.2, size=(n,)).astype(np.float32)
+    gy = rng.normal(size=(B, T, n)).astype(np.float32)
+    qv, kv = E.to_var(q), E.to_var(k)
+    wv, bv = E.to_var(w), E.to_var(b)
+    for v in (qv, kv, wv, bv):
+        v.requires_grad = True
+    assert ops.din_att_fusable(qv, kv, n)
+    tape = E.Tape()
+    with E.recording(tape):
+        y = ops.din_att_first(qv, kv, wv, bv, act)
+    out = E.contiguous(y).cpu().numpy()
+    y.requires_grad = True
+    E.add_grad(y, torch.from_numpy(gy).to(y.data.device))
+    tape.backward()
+    qt, kt, wt, bt = _t(q), _t(k), _t(w), _t(b)
+    qq = qt.expand(B, T, E_)
+    a = torch.cat([qq, kt, qq - kt, qq * kt], dim=-1)
+    want = a @ wt + bt
+    want = {"sigmoid": torch.sigmoid, "relu": torch.relu, None: lambda v: v}[act](want)
+    (want * torch.from_numpy(gy)).sum().backward()
+
+    def close(got, ref, what):
+        ref = ref.detach().numpy()
+        np.testing.assert_allclose(np.asarray(got).reshape(ref.shape), ref, rtol=2e-4,
+                                   atol=2e-4 * float(np.abs(ref).max()), err_msg=what)
+    close(out, want, "out")
+    close(qv.grad.cpu().numpy(), qt.grad, "dq")
+    close(kv.grad.cpu().numpy(), kt.grad, "dk")
+    close(wv.grad.cpu().numpy(), wt.grad, "dw")
+    close(bv.grad.cpu().numpy(), bt.grad, "db")

@@ -162,3 +162,69 @@ def test_shard_helpers():
     assert [len(p) for p in parts] == [parallel.shard_size(23, r, 4) for r in range(4)] == [6, 6, 6, 5]
     for r, p in enumerate(parts):
         assert all(v % 4 == r for v in p) and list(p // 4) == list(range(len(p)))
+
+
+def _policy_worker(rank, world, port, out):
+    """compile() under a world-2 process group decides, per table, between 'row-sharded + row-wise update' and
+    'replicated + dense all-reduced gradient' - never 'replicated + row-wise local update' (replicas would drift)."""
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        from deepctr_b200 import engine as E
+        from deepctr_b200.engine import SGD
+        from deepctr_b200.feature_column import SparseFeat, DenseFeat, VarLenSparseFeat
+        from deepctr_b200.inputs import Embedding
+        from deepctr_b200.models import DeepFM
+        # (1) Criteo shape: every table (and its dim-1 linear twin) is row-sharded
+        E.clear_session()
+        cols = [SparseFeat("C%d" % i, 41 + i, 8) for i in range(4)] + [DenseFeat("I0", 1)]
+        m = DeepFM(cols, cols, dnn_hidden_units=(8,), l2_reg_linear=0, l2_reg_embedding=0)
+        m.compile(SGD(0.1), "binary_crossentropy", embedding_update="sparse")
+        assert m.planner.sharded
+        for l in m.layers:
+            if isinstance(l, Embedding):
+                w = l.embeddings
+                assert w.sparse_grad and w.opt_state["shard"][:2] == (rank, world), l.name
+                assert w.shape[0] == (l.input_dim - rank + world - 1) // world, (l.name, w.shape)
+        # (2) a pooled VarLen feature next to them: the fast tables are sharded, the sequence table (generic
+        #     gather path) stays replicated and therefore takes the dense, all-reduced gradient path
+        E.clear_session()
+        cols2 = cols + [VarLenSparseFeat(SparseFeat("tags", 30, 8), maxlen=5, combiner="mean")]
+        m2 = DeepFM(cols2, cols2, dnn_hidden_units=(8,), l2_reg_linear=0, l2_reg_embedding=0)
+        m2.compile(SGD(0.1), "binary_crossentropy", embedding_update="sparse")
+        kinds = {}
+        for l in m2.layers:
+            if isinstance(l, Embedding):
+                w = l.embeddings
+                sharded = "shard" in w.opt_state
+                assert sharded == w.sparse_grad, (l.name, sharded, w.sparse_grad)     # never replicated + sparse
+                kinds[l.name] = sharded
+        assert kinds["sparse_seq_emb_tags"] is False and kinds["linear0sparse_seq_emb_tags"] is False
+        dense = [w.name for w in m2.trainable_weights if not w.sparse_grad]
+        assert "sparse_seq_emb_tags/embeddings" in dense          # part of the all-reduced bucket
+        # (3) sparse + L2 on the tables is refused, 'auto' warns
+        import warnings
+        m3 = DeepFM(cols, cols, dnn_hidden_units=(8,))            # builder default l2 = 1e-5
+        try:
+            m3.compile(SGD(0.1), "binary_crossentropy", embedding_update="sparse")
+            raise AssertionError("sparse update with an L2-regularised table must raise")
+        except ValueError as exc:
+            assert "L2" in str(exc)
+        out.put((rank, "ok"))
+    finally:
+        dist.destroy_process_group()
+
+
+def test_table_placement_policy_world2_gloo():
+    world = 2
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_policy_worker, args=(r, world, port, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    for p in procs:
+        p.join(timeout=120)
+    assert all(p.exitcode == 0 for p in procs), [p.exitcode for p in procs]
+    assert sorted(q.get(timeout=5) for _ in range(world)) == [(0, "ok"), (1, "ok")]

@@ -140,6 +140,8 @@ SIGNATURES = {
     "b2ctr_cin_gemm": (_i32, [C.POINTER(CinGemm), _vp, _sz, _vp]),
     "b2ctr_att_gemm_workspace_bytes": (_sz, [C.POINTER(AttGemm)]),
     "b2ctr_att_gemm": (_i32, [C.POINTER(AttGemm), _vp, _sz, _vp]),
+    "b2ctr_cin_fold": (_i32, [C.POINTER(CinGemm), _vp, _vp, _i64, _vp]),
+    "b2ctr_cin_t0_bwd": (_i32, [_vp, _i64, _vp, _i64, _i64, _i64, _i32, _i64, _i32, _i32, _vp]),
     "b2ctr_cin_t0": (_i32, [_vp, _i64, _i64, _i64, _vp, _i64, _i64, _i32, _i32, _vp]),
     "b2ctr_cin_unpad_rows": (_i32, [_vp, _vp, _i32, _i32, _i32, _i64, _vp]),
     "b2ctr_cin_sum_d": (_i32, [_vp, _i64, _i32, _i32, _i32, _vp, _i64, _i32, _i64, _vp]),

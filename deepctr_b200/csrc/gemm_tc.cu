@@ -377,6 +377,8 @@ struct PlaneArgs {
   const float* cin_t0; const float* cin_xk;
   int64_t cin_ld0, cin_ldk, cin_rows;
   int cin_m, cin_h, cin_hp, cin_on;
+  // FOLD epilogue (CIN backward): dT0 [rows, cin_ld0] and dXk [rows, fold_ldx], both accumulated with red.add
+  float* fold_dt0; float* fold_dxk; int64_t fold_ldx;
 };
 
 // dst planes [rows_pad, k_pad] <- src(r, k) = p[r*sr + k*sk]; zero outside [rows, k).
@@ -671,7 +673,6 @@ static cudaError_t launch_planes(const PlaneArgs& pa, cudaStream_t st) {
 // (neighbouring clusters share the A rows through L2).
 // ================================================================================================
 constexpr int kWsEpilogueWarps = 8;
-constexpr int kWsThreads = (kWsEpilogueWarps + 4 + 1) * 32;
 constexpr int kWsProducers = 4;   // warps
 
 struct WsArgs {
@@ -762,52 +763,66 @@ __device__ __forceinline__ void tma_prefetch_desc(const CUtensorMap* map) {
   asm volatile("prefetch.tensormap [%0];" ::"l"(map) : "memory");
 }
 
-// One producer thread = one row r of the outer product: 64 consecutive q = i*hp + j starting at q0 (hp is 32 or a
-// multiple of 64, so 8-element chunks never straddle an i), split into bf16 hi/lo and stored as eight 16-byte
-// chunks of the 128-byte-swizzled row `rr` of the stage (rr & 7 selects the XOR pattern).
-__device__ __forceinline__ void cin_generate_row(const PlaneArgs& g, int64_t r, int64_t q0, unsigned char* hi_row,
-                                                 unsigned char* lo_row, int rr) {
+// fp32 pair -> bf16 hi pair + bf16 lo pair (v = hi + lo up to 2^-17): two cvt.rn.bf16x2.f32 + four ALU ops
+__device__ __forceinline__ void split_pair(float v0, float v1, uint32_t& h, uint32_t& l) {
+  const __nv_bfloat162 hh = __floats2bfloat162_rn(v0, v1);        // .x = v0 in the low half
+  h = *reinterpret_cast<const uint32_t*>(&hh);
+  const float h0 = __uint_as_float(h << 16), h1 = __uint_as_float(h & 0xffff0000u);
+  const __nv_bfloat162 ll = __floats2bfloat162_rn(v0 - h0, v1 - h1);
+  l = *reinterpret_cast<const uint32_t*>(&ll);
+}
+__device__ __forceinline__ void store_chunk(const float (&v)[8], unsigned char* hi_row, unsigned char* lo_row, int off) {
+  uint32_t h[4], l[4];
+#pragma unroll
+  for (int e = 0; e < 4; ++e) split_pair(v[2 * e], v[2 * e + 1], h[e], l[e]);
+  *reinterpret_cast<uint4*>(hi_row + off) = make_uint4(h[0], h[1], h[2], h[3]);
+  *reinterpret_cast<uint4*>(lo_row + off) = make_uint4(l[0], l[1], l[2], l[3]);
+}
+
+// Generated A operand, CIN: one producer thread = half a row r of the outer product per stage: 32 consecutive
+// q = i*hp + j starting at q0 (a multiple of 32; hp is 32 or a multiple of 64, so 8-element chunks never straddle
+// an i), split into bf16 hi/lo and stored as four 16-byte chunks [c0, c0+4) of the 128-byte-swizzled row `rr`.
+__device__ __forceinline__ void cin_generate_half(const PlaneArgs& g, int64_t r, int q0, unsigned char* hi_row,
+                                                  unsigned char* lo_row, int rr, int c0) {
   const bool row_ok = r < g.cin_rows;
   const float* xk = g.cin_xk + r * g.cin_ldk;
   const float* t0 = g.cin_t0 + r * g.cin_ld0;
+  const int hp = g.cin_hp, h = g.cin_h;
+  int i = q0 / hp, j = q0 - i * hp;
+  float a = (row_ok && i < g.cin_m) ? __ldg(t0 + i) : 0.f;
+  float4 x[8];
 #pragma unroll
-  for (int c = 0; c < 8; ++c) {
-    const int64_t q = q0 + 8 * c;
-    const int i = (int)(q / g.cin_hp), j = (int)(q - (int64_t)i * g.cin_hp);
-    float v[8];
-    if (row_ok && i < g.cin_m && j < g.cin_h) {
-      const float a = __ldg(t0 + i);
-      // h % 4 == 0 and j % 8 == 0: the first quad is inside the row whenever j < h; the second may not be
-      const float4 x0 = __ldg(reinterpret_cast<const float4*>(xk + j));
-      const float4 x1 = j + 4 < g.cin_h ? __ldg(reinterpret_cast<const float4*>(xk + j) + 1) : make_float4(0.f, 0.f, 0.f, 0.f);
-      v[0] = a * x0.x; v[1] = a * x0.y; v[2] = a * x0.z; v[3] = a * x0.w;
-      v[4] = a * x1.x; v[5] = a * x1.y; v[6] = a * x1.z; v[7] = a * x1.w;
+  for (int c = 0; c < 4; ++c) {          // all eight 16-byte loads first (independent of a)
+    const int jj = j + 8 * c >= hp ? j + 8 * c - hp : j + 8 * c;
+    // h % 4 == 0 or the rows are padded to hp: a quad starting below h is inside the row
+    x[2 * c] = (row_ok && jj < h) ? __ldg(reinterpret_cast<const float4*>(xk + jj)) : make_float4(0.f, 0.f, 0.f, 0.f);
+    x[2 * c + 1] = (row_ok && jj + 4 < h) ? __ldg(reinterpret_cast<const float4*>(xk + jj) + 1)
+                                          : make_float4(0.f, 0.f, 0.f, 0.f);
+  }
+#pragma unroll
+  for (int c = 0; c < 4; ++c) {
+    float v[8] = {a * x[2 * c].x, a * x[2 * c].y, a * x[2 * c].z, a * x[2 * c].w,
+                  a * x[2 * c + 1].x, a * x[2 * c + 1].y, a * x[2 * c + 1].z, a * x[2 * c + 1].w};
+    if (h & 7) {                         // ragged h: zero the tail of the last chunk
 #pragma unroll
       for (int e = 0; e < 8; ++e)
-        if (j + e >= g.cin_h) v[e] = 0.f;
-    } else {
-#pragma unroll
-      for (int e = 0; e < 8; ++e) v[e] = 0.f;
+        if (j + e >= h) v[e] = 0.f;
     }
-    uint32_t h[4], l[4];
-#pragma unroll
-    for (int e = 0; e < 4; ++e) {
-      const __nv_bfloat16 h0 = __float2bfloat16_rn(v[2 * e]), h1 = __float2bfloat16_rn(v[2 * e + 1]);
-      h[e] = pack_bf16(h0, h1);
-      l[e] = pack_bf16(__float2bfloat16_rn(v[2 * e] - __bfloat162float(h0)),
-                       __float2bfloat16_rn(v[2 * e + 1] - __bfloat162float(h1)));
+    store_chunk(v, hi_row, lo_row, ((c0 + c) ^ (rr & 7)) << 4);
+    j += 8;
+    if (j >= hp) {                       // next i (only when hp == 32: two i per 64-deep k-block)
+      j = 0;
+      ++i;
+      a = (row_ok && i < g.cin_m) ? __ldg(t0 + i) : 0.f;
     }
-    const int off = (c ^ (rr & 7)) << 4;
-    *reinterpret_cast<uint4*>(hi_row + off) = make_uint4(h[0], h[1], h[2], h[3]);
-    *reinterpret_cast<uint4*>(lo_row + off) = make_uint4(l[0], l[1], l[2], l[3]);
   }
 }
 
 // DIN local-activation-unit input (deepctr/layers/core.py:96-101), generated the same way: row r = (b, t),
 //   A[r, :] = [ q_b , k_bt , q_b - k_bt , q_b * k_bt ]   (4 segments of E columns; E % 8 == 0)
 // cin_t0 = queries [B, ld0], cin_xk = keys (sample stride cin_ldk, row stride E), cin_m = T, cin_h = E.
-__device__ __forceinline__ void att_generate_row(const PlaneArgs& g, int64_t r, int64_t c0, unsigned char* hi_row,
-                                                 unsigned char* lo_row, int rr) {
+__device__ __forceinline__ void att_generate_half(const PlaneArgs& g, int64_t r, int col0, unsigned char* hi_row,
+                                                  unsigned char* lo_row, int rr, int c0) {
   const int T = g.cin_m, E = g.cin_h;
   const bool row_ok = r < g.cin_rows;
   const int64_t b = row_ok ? r / T : 0;
@@ -815,48 +830,42 @@ __device__ __forceinline__ void att_generate_row(const PlaneArgs& g, int64_t r, 
   const float* q = g.cin_t0 + b * g.cin_ld0;
   const float* k = g.cin_xk + b * g.cin_ldk + (int64_t)t * E;
 #pragma unroll
-  for (int c = 0; c < 8; ++c) {
-    const int64_t col = c0 + 8 * c;
-    const int seg = (int)(col / E), e = (int)(col - (int64_t)seg * E);
+  for (int c = 0; c < 4; ++c) {
+    const int col = col0 + 8 * c;
+    const int seg = col / E, e = col - seg * E;
     float v[8];
     if (row_ok && seg < 4) {
-      float qa[8], ka[8];
-      if (seg != 1) {
-        const float4 a0 = __ldg(reinterpret_cast<const float4*>(q + e)), a1 = __ldg(reinterpret_cast<const float4*>(q + e) + 1);
-        qa[0] = a0.x; qa[1] = a0.y; qa[2] = a0.z; qa[3] = a0.w; qa[4] = a1.x; qa[5] = a1.y; qa[6] = a1.z; qa[7] = a1.w;
-      }
-      if (seg != 0) {
-        const float4 b0 = __ldg(reinterpret_cast<const float4*>(k + e)), b1 = __ldg(reinterpret_cast<const float4*>(k + e) + 1);
-        ka[0] = b0.x; ka[1] = b0.y; ka[2] = b0.z; ka[3] = b0.w; ka[4] = b1.x; ka[5] = b1.y; ka[6] = b1.z; ka[7] = b1.w;
-      }
+      float4 a0 = make_float4(0.f, 0.f, 0.f, 0.f), a1 = a0, b0 = a0, b1 = a0;
+      if (seg != 1) { a0 = __ldg(reinterpret_cast<const float4*>(q + e)); a1 = __ldg(reinterpret_cast<const float4*>(q + e) + 1); }
+      if (seg != 0) { b0 = __ldg(reinterpret_cast<const float4*>(k + e)); b1 = __ldg(reinterpret_cast<const float4*>(k + e) + 1); }
+      const float qa[8] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w};
+      const float ka[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
 #pragma unroll
-      for (int j = 0; j < 8; ++j)
-        v[j] = seg == 0 ? qa[j] : seg == 1 ? ka[j] : seg == 2 ? __fsub_rn(qa[j], ka[j]) : __fmul_rn(qa[j], ka[j]);
+      for (int jx = 0; jx < 8; ++jx)
+        v[jx] = seg == 0 ? qa[jx] : seg == 1 ? ka[jx] : seg == 2 ? __fsub_rn(qa[jx], ka[jx]) : __fmul_rn(qa[jx], ka[jx]);
     } else {
 #pragma unroll
-      for (int j = 0; j < 8; ++j) v[j] = 0.f;
+      for (int jx = 0; jx < 8; ++jx) v[jx] = 0.f;
     }
-    uint32_t h[4], l[4];
-#pragma unroll
-    for (int j = 0; j < 4; ++j) {
-      const __nv_bfloat16 h0 = __float2bfloat16_rn(v[2 * j]), h1 = __float2bfloat16_rn(v[2 * j + 1]);
-      h[j] = pack_bf16(h0, h1);
-      l[j] = pack_bf16(__float2bfloat16_rn(v[2 * j] - __bfloat162float(h0)),
-                       __float2bfloat16_rn(v[2 * j + 1] - __bfloat162float(h1)));
-    }
-    const int off = (c ^ (rr & 7)) << 4;
-    *reinterpret_cast<uint4*>(hi_row + off) = make_uint4(h[0], h[1], h[2], h[3]);
-    *reinterpret_cast<uint4*>(lo_row + off) = make_uint4(l[0], l[1], l[2], l[3]);
+    store_chunk(v, hi_row, lo_row, ((c0 + c) ^ (rr & 7)) << 4);
   }
 }
-__device__ __forceinline__ void generate_row(const PlaneArgs& g, int64_t r, int64_t q0, unsigned char* hi_row,
-                                             unsigned char* lo_row, int rr) {
-  if (g.cin_on == 2) att_generate_row(g, r, q0, hi_row, lo_row, rr);
-  else cin_generate_row(g, r, q0, hi_row, lo_row, rr);
+__device__ __forceinline__ void generate_half(const PlaneArgs& g, int64_t r, int q0, unsigned char* hi_row,
+                                              unsigned char* lo_row, int rr, int c0) {
+  if (g.cin_on == 2) att_generate_half(g, r, q0, hi_row, lo_row, rr, c0);
+  else cin_generate_half(g, r, q0, hi_row, lo_row, rr, c0);
 }
 
-template <int BN, int STAGES, int NCTA, bool TMA, bool CIN = false>
-__global__ void __launch_bounds__(kWsThreads, 1)
+// generated-operand kernels run 8 producer warps (two threads per generated row), the others 4
+template <bool CIN>
+struct WsLayout {
+  static constexpr int kProducers = CIN ? 8 : kWsProducers;
+  static constexpr int kMmaWarp = kWsEpilogueWarps + kProducers;
+  static constexpr int kThreads = (kMmaWarp + 1) * 32;
+};
+
+template <int BN, int STAGES, int NCTA, bool TMA, bool CIN = false, bool FOLD = false>
+__global__ void __launch_bounds__(WsLayout<CIN>::kThreads, 1)
     gemm_planes_ws_kernel(const __grid_constant__ WsArgs w, const __grid_constant__ CUtensorMap tm_ah,
                           const __grid_constant__ CUtensorMap tm_al, const __grid_constant__ CUtensorMap tm_bh,
                           const __grid_constant__ CUtensorMap tm_bl) {
@@ -880,7 +889,7 @@ __global__ void __launch_bounds__(kWsThreads, 1)
     for (int s = 0; s < STAGES; ++s) {
       // cp.async producers: one deferred arrival per producer thread of THIS CTA; TMA: one arrive.expect_tx
       // CIN: the B planes arrive by TMA (1 arrive.expect_tx) + one arrival per generating thread
-      mbar_init(&full_bar[s], CIN ? 1 + kWsProducers * 32 : (TMA ? 1 : kWsProducers * 32));
+      mbar_init(&full_bar[s], CIN ? 1 + WsLayout<CIN>::kProducers * 32 : (TMA ? 1 : kWsProducers * 32));
       mbar_init(&peer_full[s], 1);                    // leader only: the peer CTA's half of the stage landed
       mbar_init(&empty_bar[s], 1);
     }
@@ -890,7 +899,7 @@ __global__ void __launch_bounds__(kWsThreads, 1)
     }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
-  if (warp == kWsEpilogueWarps + kWsProducers) {
+  if (warp == WsLayout<CIN>::kMmaWarp) {
     if constexpr (NCTA == 1) {
       asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_slot)),
                    "r"(TMEM_COLS)
@@ -911,6 +920,16 @@ __global__ void __launch_bounds__(kWsThreads, 1)
 
   // tile -> coordinates (N tile fastest, then M, then the split-K slice)
   auto decode = [&](int64_t tile, int64_t& mt, int64_t& nt, int64_t& kbeg, int& nkb) {
+    if constexpr (FOLD) {
+      // a cluster owns whole ROW BLOCKS and walks all their N tiles in turn (its epilogue accumulates across
+      // them): work item j of cluster c is (row block c + (j / tiles_n) * nclusters, N tile j % tiles_n)
+      const int64_t j = tile / nclusters;
+      nt = j % w.tiles_n;
+      mt = tile % nclusters + (j / w.tiles_n) * nclusters;
+      kbeg = 0;
+      nkb = mt < w.tiles_m ? (int)(g.k_pad / kTK) : 0;
+      return;
+    }
     nt = tile % w.tiles_n;
     const int64_t rest = tile / w.tiles_n;
     mt = rest % w.tiles_m;
@@ -920,7 +939,7 @@ __global__ void __launch_bounds__(kWsThreads, 1)
     nkb = kend > kbeg ? (int)((kend - kbeg) / kTK) : 0;
   };
 
-  constexpr int kMmaWarp = kWsEpilogueWarps + kWsProducers;
+  constexpr int kMmaWarp = WsLayout<CIN>::kMmaWarp;
   if (CIN && warp >= kWsEpilogueWarps && warp < kMmaWarp) {
     // ------------------------------------------------------------------------------ CIN producers
     // B (filter / dY planes) by TMA from thread 0; A generated in place by all 128 producer threads.
@@ -953,12 +972,14 @@ __global__ void __launch_bounds__(kWsThreads, 1)
             tma_load_2d(st + 2 * A_PLANE + B_PLANE, &tm_bl, (int32_t)k0, n0, bar);
           }
         }
-        if (g.a_mn) {      // A^T: M = q (two 64-wide atoms), K = r: thread -> (atom, k-row)
-          const int atom = tid >> 6, rr = tid & 63;
-          generate_row(g, k0 + rr, m0 + atom * 64, stp + atom * 8192 + rr * 128,
-                       stp + A_PLANE + atom * 8192 + rr * 128, rr);
-        } else {           // A: M = r, K = q: thread -> row
-          generate_row(g, m0 + tid, k0, stp + tid * 128, stp + A_PLANE + tid * 128, tid);
+        const int half = tid & 1;           // two threads per generated row: 32 of its 64 columns each
+        if (g.a_mn) {      // A^T: M = q (two 64-wide atoms), K = r: thread -> (atom, k-row, half)
+          const int atom = tid >> 7, rr = (tid & 127) >> 1;
+          generate_half(g, k0 + rr, (int)(m0 + atom * 64 + half * 32), stp + atom * 8192 + rr * 128,
+                        stp + A_PLANE + atom * 8192 + rr * 128, rr, half * 4);
+        } else {           // A: M = r, K = q: thread -> (row, half)
+          const int rr = tid >> 1;
+          generate_half(g, m0 + rr, (int)(k0 + half * 32), stp + rr * 128, stp + A_PLANE + rr * 128, rr, half * 4);
         }
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
         mbar_arrive(&full_bar[s]);
@@ -1137,6 +1158,91 @@ __global__ void __launch_bounds__(kWsThreads, 1)
                        (!g.bias || (reinterpret_cast<uintptr_t>(g.bias) & 15) == 0);
     const bool vec_ws = (g.n % 4 == 0);
     uint32_t acc_it = 0;
+    if constexpr (FOLD) {
+      // CIN backward: the accumulator tile is dZ[r, q] (q = i*hp + j) = dY W'^T and is never stored - it is folded
+      // onto the two factors of the outer product right here:
+      //   dT0[r, i] += sum_j dZ[r, i*hp + j] * xk[r, j]          (one red.add per 32-column group)
+      //   dXk[r, j] += sum_i dZ[r, i*hp + j] * t0[r, i]          (registers across the N tiles of the row block,
+      //                                                           red.add.v4 once per row block)
+      // BN % hp == 0, so a thread's column groups keep their j-range from tile to tile.
+      constexpr int GROUPS = COLS / 32;
+      float dxk[GROUPS][32];
+      for (int64_t tile = cluster_id; tile < w.ntiles; tile += nclusters) {
+        int64_t mt, nt, kbeg;
+        int nkb;
+        decode(tile, mt, nt, kbeg, nkb);
+        if (nkb == 0) continue;
+        const uint32_t ab = acc_it & 1;
+        mbar_wait(&acc_full[ab], (acc_it >> 1) & 1);
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        const int64_t gm = (mt * NCTA + cta_rank) * kTM + sub * 32 + lane;
+        const bool row_ok = gm < g.m;
+        const float* t0 = g.cin_t0 + (row_ok ? gm : 0) * g.cin_ld0;
+        const float* xk = g.cin_xk + (row_ok ? gm : 0) * g.cin_ldk;
+        if (nt == 0) {
+#pragma unroll
+          for (int gi = 0; gi < GROUPS; ++gi)
+#pragma unroll
+            for (int jx = 0; jx < 32; ++jx) dxk[gi][jx] = 0.f;
+        }
+#pragma unroll
+        for (int gi = 0; gi < GROUPS; ++gi) {
+          const int c0 = half * COLS + gi * 32;
+          const int64_t q = nt * BN + c0;
+          if (q < g.n) {                   // warp-uniform
+            uint32_t r[32];
+            const uint32_t taddr = tmem_base + ((uint32_t)(sub * 32) << 16) + ab * BN + (uint32_t)c0;
+            asm volatile(
+                "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+                "{%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,"
+                "%16,%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,%29,%30,%31}, [%32];\n"
+                : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]),
+                  "=r"(r[7]), "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]),
+                  "=r"(r[14]), "=r"(r[15]), "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]),
+                  "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]),
+                  "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+                : "r"(taddr));
+            asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+            const int i = (int)(q / g.cin_hp), j0 = (int)(q - (int64_t)i * g.cin_hp);
+            if (row_ok && i < g.cin_m) {
+              const float a = __ldg(t0 + i);
+              float p = 0.f;
+#pragma unroll
+              for (int jx = 0; jx < 32; jx += 4) {
+                float4 xv = make_float4(0.f, 0.f, 0.f, 0.f);
+                if (j0 + jx < g.cin_h) xv = __ldg(reinterpret_cast<const float4*>(xk + j0 + jx));
+                const float d0 = __uint_as_float(r[jx]), d1 = __uint_as_float(r[jx + 1]);
+                const float d2 = __uint_as_float(r[jx + 2]), d3 = __uint_as_float(r[jx + 3]);
+                if (j0 + jx + 1 >= g.cin_h) xv.y = 0.f;       // ragged h (rows padded to hp: loads stay in bounds)
+                if (j0 + jx + 2 >= g.cin_h) xv.z = 0.f;
+                if (j0 + jx + 3 >= g.cin_h) xv.w = 0.f;
+                p += d0 * xv.x + d1 * xv.y + d2 * xv.z + d3 * xv.w;
+                dxk[gi][jx] += d0 * a; dxk[gi][jx + 1] += d1 * a; dxk[gi][jx + 2] += d2 * a; dxk[gi][jx + 3] += d3 * a;
+              }
+              red_add_f1(g.fold_dt0 + gm * g.cin_ld0 + i, p);
+            }
+          }
+        }
+        if (nt == w.tiles_n - 1 && row_ok) {
+#pragma unroll
+          for (int gi = 0; gi < GROUPS; ++gi) {
+            const int j0 = (half * COLS + gi * 32) % g.cin_hp;
+            float* dst = g.fold_dxk + gm * g.fold_ldx + j0;
+#pragma unroll
+            for (int jx = 0; jx < 32; jx += 4)
+              if (j0 + jx < g.cin_h)
+                red_add_f4(dst + jx, make_float4(dxk[gi][jx], dxk[gi][jx + 1], dxk[gi][jx + 2], dxk[gi][jx + 3]));
+          }
+        }
+        asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+        __syncwarp();
+        if (lane == 0) {
+          if (NCTA == 1 || cta_rank == 0) mbar_arrive(&acc_empty[ab]);
+          else mbar_arrive_cluster(&acc_empty[ab], 0);
+        }
+        ++acc_it;
+      }
+    } else
     for (int64_t tile = cluster_id; tile < w.ntiles; tile += nclusters) {
       int64_t mt, nt, kbeg;
       int nkb;
@@ -1236,7 +1342,7 @@ __global__ void __launch_bounds__(kWsThreads, 1)
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
   __syncthreads();
   if constexpr (NCTA > 1) cluster_sync_all();      // no CTA leaves while its peer may still signal it
-  if (warp == kWsEpilogueWarps + kWsProducers) {
+  if (warp == WsLayout<CIN>::kMmaWarp) {
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
     if constexpr (NCTA == 1)
       asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(TMEM_COLS) : "memory");
@@ -1250,18 +1356,23 @@ struct TmaMaps {
   bool ok;
 };
 
-template <int BN, int STAGES, int NCTA, bool TMA, bool CIN = false>
+template <int BN, int STAGES, int NCTA, bool TMA, bool CIN = false, bool FOLD = false>
 static cudaError_t launch_ws_impl(const WsArgs& wa, const TmaMaps& tm, cudaStream_t st) {
   constexpr size_t smem = (size_t)STAGES * (2 * kTM * 128 + 2 * (BN / NCTA) * 128) + 1024;
   static_assert(smem + 256 <= 227 * 1024, "stage ring exceeds shared memory");
-  auto kern = gemm_planes_ws_kernel<BN, STAGES, NCTA, TMA, CIN>;
+  auto kern = gemm_planes_ws_kernel<BN, STAGES, NCTA, TMA, CIN, FOLD>;
   cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) return e;
   const int64_t max_clusters = kNumSMs / NCTA;
-  const int64_t nclusters = wa.ntiles < max_clusters ? wa.ntiles : max_clusters;
+  int64_t nclusters = wa.ntiles < max_clusters ? wa.ntiles : max_clusters;
+  WsArgs wcopy = wa;
+  if (FOLD) {      // clusters own row blocks: ntiles = work-item slots of the round-robin over row blocks
+    nclusters = wa.tiles_m < max_clusters ? wa.tiles_m : max_clusters;
+    wcopy.ntiles = ceil_div(wa.tiles_m, nclusters) * wa.tiles_n * nclusters;
+  }
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = dim3((unsigned)(nclusters * NCTA));
-  cfg.blockDim = dim3(kWsThreads);
+  cfg.blockDim = dim3(WsLayout<CIN>::kThreads);
   cfg.dynamicSmemBytes = smem;
   cfg.stream = st;
   cudaLaunchAttribute attr[1];
@@ -1271,7 +1382,7 @@ static cudaError_t launch_ws_impl(const WsArgs& wa, const TmaMaps& tm, cudaStrea
   attr[0].val.clusterDim.z = 1;
   cfg.attrs = attr;
   cfg.numAttrs = 1;
-  return cudaLaunchKernelEx(&cfg, kern, wa, tm.ah, tm.al, tm.bh, tm.bl);
+  return cudaLaunchKernelEx(&cfg, kern, wcopy, tm.ah, tm.al, tm.bh, tm.bl);
 }
 template <int BN, int STAGES, int NCTA>
 static cudaError_t launch_ws(const WsArgs& wa, const TmaMaps& tm, cudaStream_t st) {
@@ -1354,6 +1465,14 @@ static b2ctr_status_t gemm_planes(const b2ctr_gemm_t* g, void* workspace, size_t
   const bool ws_kernel = tc_variant(g) == 4;
   int bn = ws_kernel ? (g->n <= 32 ? 32 : g->n <= 64 ? 64 : g->n <= 128 ? 128 : 256)
                      : planes_bn(g->n, g->k / (g->split_k > 1 ? g->split_k : 1));
+  if (ws_kernel && bn == 256) {
+    // ragged N (dgrad of the first DNN layer: N = 845): 256-wide tiles pad it to 1024 (17 % of the MMAs and of the
+    // epilogue work are dead), 128-wide tiles to 896 (6 %).  Take the narrower tile when it saves > 8 % of the tile area.
+    static int tail = -1;
+    if (tail < 0) { const char* ev = getenv("B2CTR_TC_BN_TAIL"); tail = ev ? atoi(ev) : 1; }
+    const int64_t a256 = round_up(g->n, 256), a128 = round_up(g->n, 128);
+    if (tail && (a256 - a128) * 100 > 8 * a256) bn = 128;
+  }
   const int64_t kp = round_up(g->k > 0 ? g->k : 1, kTK), mp = round_up(g->m, 2 * kTM);
   unsigned char* w = (unsigned char*)workspace;
   float* ws = (float*)w;
@@ -1418,6 +1537,7 @@ static b2ctr_status_t gemm_planes(const b2ctr_gemm_t* g, void* workspace, size_t
   pa.k_per_split = ceil_div(ceil_div(kp, splits), kTK) * kTK;
   pa.alpha = g->alpha; pa.act = g->act; pa.accumulate = g->accumulate; pa.splits = splits;
   pa.cin_on = 0; pa.cin_t0 = pa.cin_xk = nullptr; pa.cin_ld0 = pa.cin_ldk = pa.cin_rows = 0; pa.cin_m = pa.cin_h = pa.cin_hp = 0;
+  pa.fold_dt0 = pa.fold_dxk = nullptr; pa.fold_ldx = 0;
   cudaError_t e;
   const bool short_k = pa.k_per_split <= 4 * kTK;
   if (ws_kernel) {
@@ -1531,6 +1651,7 @@ static b2ctr_status_t gen_gemm(const GenSpec& sp, int mode, int64_t n, const voi
   pa.a_hi = pa.a_lo = nullptr; pa.a_pitch = 0;
   pa.cin_on = sp.kind; pa.cin_t0 = sp.p0; pa.cin_xk = sp.p1; pa.cin_ld0 = sp.ld0; pa.cin_ldk = sp.ld1;
   pa.cin_rows = sp.rows; pa.cin_m = sp.m; pa.cin_h = sp.h; pa.cin_hp = sp.hp;
+  pa.fold_dt0 = pa.fold_dxk = nullptr; pa.fold_ldx = 0;
   pa.b_mn = 1;      // both B operands are row-major matrices whose reduction dim is their row index
   pa.c = c; pa.bias = bias; pa.ws = (float*)workspace; pa.ldc = ldc;
   pa.alpha = 1.f; pa.act = act; pa.accumulate = 0; pa.splits = splits;
@@ -1603,6 +1724,54 @@ b2ctr_status_t cin_gemm(const b2ctr_cin_gemm_t* g, void* workspace, size_t works
   B2_REQUIRE(g->mode == 0 ? g->w_planes != nullptr : g->dy_planes != nullptr, "cin_gemm: operand planes missing");
   return gen_gemm(cin_spec(g), g->mode, g->n, g->mode == 0 ? g->w_planes : g->dy_planes, g->c, g->ldc, g->bias, g->act,
                   g->split_k, workspace, workspace_bytes, st, "b2ctr_cin_gemm");
+}
+
+// CIN backward, data gradient: dZ = dY W'^T folded onto T0 and X_k inside the epilogue (FOLD kernel).
+// dY given as K-major planes of [rows, n]; W' planes (b2ctr_cin_filter_planes) read K-major (rows = q).
+b2ctr_status_t cin_fold(const b2ctr_cin_gemm_t* g, float* dt0, float* dxk, int64_t ldx, cudaStream_t st) {
+  B2_REQUIRE(g && g->t0 && g->xk && g->w_planes && g->dy_planes && dt0 && dxk, "cin_fold: bad arguments");
+  B2_REQUIRE(g->hp == 32 || g->hp == 64 || g->hp == 128, "cin_fold: hp must be 32, 64 or 128");
+  B2_REQUIRE(g->ldk % 4 == 0 && ldx % 4 == 0 && ((uintptr_t)dxk & 15) == 0 && ((uintptr_t)g->xk & 15) == 0 &&
+                 (g->h % 4 == 0 || (g->ldk >= g->hp && ldx >= g->hp)) && ldx >= g->h,
+             "cin_fold: xk / dxk rows must be 16-byte aligned (and padded to hp when h is not a multiple of 4)");
+  const int64_t kq = (int64_t)g->m * g->hp;
+  PlaneArgs pa;
+  const int64_t cpn = planes_cols_pad(g->n);
+  const __nv_bfloat16* ap = (const __nv_bfloat16*)g->dy_planes;
+  const int64_t a_prows = round_up(g->rows, 256);
+  pa.a_hi = ap; pa.a_lo = ap + a_prows * cpn; pa.a_pitch = cpn; pa.a_mn = 0;
+  const __nv_bfloat16* bp = (const __nv_bfloat16*)g->w_planes;
+  const int64_t b_prows = round_up(kq, 256);
+  pa.b_hi = bp; pa.b_lo = bp + b_prows * cpn; pa.b_pitch = cpn; pa.b_mn = 0;
+  pa.c = nullptr; pa.bias = nullptr; pa.ws = nullptr; pa.ldc = 0;
+  pa.m = g->rows; pa.n = kq; pa.k_pad = round_up(g->n, kTK);
+  pa.k_per_split = pa.k_pad; pa.alpha = 1.f; pa.act = 0; pa.accumulate = 0; pa.splits = 1;
+  pa.cin_on = 0; pa.cin_t0 = g->t0; pa.cin_xk = g->xk; pa.cin_ld0 = g->ld0; pa.cin_ldk = g->ldk; pa.cin_rows = g->rows;
+  pa.cin_m = g->m; pa.cin_h = g->h; pa.cin_hp = g->hp;
+  pa.fold_dt0 = dt0; pa.fold_dxk = dxk; pa.fold_ldx = ldx;
+  constexpr int bn = 128;
+  const int ncta = g->rows > kTM ? 2 : 1;
+  WsArgs wa;
+  wa.p = pa;
+  wa.tiles_m = (int)ceil_div(g->rows, (int64_t)kTM * ncta);
+  wa.tiles_n = (int)ceil_div(kq, bn);
+  wa.ntiles = (int64_t)wa.tiles_m * wa.tiles_n;
+  TmaMaps tm;
+  const int bnh = bn / ncta;
+  tm.ok = tma_map_2d(&tm.ah, pa.a_hi, cpn, a_prows, cpn, 64, kTM) && tma_map_2d(&tm.al, pa.a_lo, cpn, a_prows, cpn, 64, kTM) &&
+          tma_map_2d(&tm.bh, pa.b_hi, cpn, b_prows, cpn, 64, bnh) && tma_map_2d(&tm.bl, pa.b_lo, cpn, b_prows, cpn, 64, bnh);
+  if (!tm.ok) {
+    set_error("cin_fold: cuTensorMapEncodeTiled unavailable");
+    return B2CTR_ERR_UNSUPPORTED;
+  }
+  cudaError_t e = ncta == 2 ? launch_ws_impl<128, 4, 2, true, false, true>(wa, tm, st)
+                            : launch_ws_impl<128, 3, 1, true, false, true>(wa, tm, st);
+  if (e != cudaSuccess) {
+    set_error("b2ctr_cin_fold: CUDA launch failed: %s", cudaGetErrorString(e));
+    return B2CTR_ERR_CUDA;
+  }
+  count_launch();
+  return B2CTR_OK;
 }
 
 static GenSpec att_spec(const b2ctr_att_gemm_t* g) {
@@ -1697,6 +1866,9 @@ b2ctr_status_t b2ctr_cin_filter_planes(const float* w, int32_t m, int32_t h, int
 size_t b2ctr_cin_gemm_workspace_bytes(const b2ctr_cin_gemm_t* g) { return g ? b2ctr::cin_gemm_workspace_bytes(g) : 0; }
 b2ctr_status_t b2ctr_cin_gemm(const b2ctr_cin_gemm_t* g, void* workspace, size_t workspace_bytes, void* stream) {
   return b2ctr::cin_gemm(g, workspace, workspace_bytes, (cudaStream_t)stream);
+}
+b2ctr_status_t b2ctr_cin_fold(const b2ctr_cin_gemm_t* g, float* dt0, float* dxk, int64_t ldx, void* stream) {
+  return b2ctr::cin_fold(g, dt0, dxk, ldx, (cudaStream_t)stream);
 }
 size_t b2ctr_att_gemm_workspace_bytes(const b2ctr_att_gemm_t* g) { return g ? b2ctr::att_gemm_workspace_bytes(g) : 0; }
 b2ctr_status_t b2ctr_att_gemm(const b2ctr_att_gemm_t* g, void* workspace, size_t workspace_bytes, void* stream) {

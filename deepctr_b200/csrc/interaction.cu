@@ -98,6 +98,21 @@ __global__ void __launch_bounds__(256)
     t0[t] = i < m ? x0.p[b * x0.sb + i * x0.si + dd * x0.sd] : 0.f;
   }
 }
+// dX0(b,i,d) (+)= dT0[(b,d), i]: the factor-table gradient back in the caller's [B, m, D] layout
+__global__ void __launch_bounds__(256)
+    cin_t0_bwd_kernel(const float* __restrict__ dt0, int64_t ld0, float* dx, int64_t gb, int64_t gi, int64_t gd,
+                      int acc, int64_t nb, int m, int d) {
+  const int64_t total = nb * d * m;
+  for (int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; t < total; t += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t row = t / m;
+    const int i = (int)(t - row * m);
+    const int64_t b = row / d;
+    const int dd = (int)(row - b * d);
+    float* o = dx + b * gb + i * gi + dd * gd;
+    const float v = dt0[row * ld0 + i];
+    *o = acc ? *o + v : v;
+  }
+}
 __global__ void __launch_bounds__(256)
     cin_unpad_rows_kernel(const float* __restrict__ src, float* dst, int m, int h, int hp, int64_t n) {
   const int64_t total = (int64_t)m * h * n;
@@ -364,6 +379,15 @@ b2ctr_status_t b2ctr_cin_t0(const float* x0, int64_t s0b, int64_t s0i, int64_t s
   CinView a{x0, s0b, s0i, s0d};
   cin_t0_kernel<<<grid_for(nb * d * ld0, 256, 8), 256, 0, ST>>>(a, t0, ld0, nb, m, d);
   B2_CHECK_LAUNCH("b2ctr_cin_t0");
+  return B2CTR_OK;
+}
+
+b2ctr_status_t b2ctr_cin_t0_bwd(const float* dt0, int64_t ld0, float* dx, int64_t gb, int64_t gi, int64_t gd,
+                                int32_t accumulate, int64_t nb, int32_t m, int32_t d, void* stream) {
+  B2_REQUIRE(dt0 && dx && m > 0 && d > 0 && ld0 >= m, "cin_t0_bwd: bad arguments");
+  if (nb <= 0) return B2CTR_OK;
+  cin_t0_bwd_kernel<<<grid_for(nb * d * m, 256, 8), 256, 0, ST>>>(dt0, ld0, dx, gb, gi, gd, accumulate, nb, m, d);
+  B2_CHECK_LAUNCH("b2ctr_cin_t0_bwd");
   return B2CTR_OK;
 }
 

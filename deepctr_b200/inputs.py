@@ -778,6 +778,7 @@ class EmbeddingPlanner(object):
 
     def _backward_generic(self, feed, bufs, generic, opt, batch):
         feats, scales = [], []
+        flat = {}            # (rows, scale) -> features of plain sequences re-described as B*T single lookups
         for s in generic:
             if not s.emb.embeddings.trainable:
                 continue
@@ -786,11 +787,24 @@ class EmbeddingPlanner(object):
                 continue
             tgt, scale = _grad_target(s.emb.embeddings, opt)
             src = s.emb.embeddings.data if s.pool == L.POOL_MAX else None
-            feats.append(self._feature(s, feed, buf.grad, buf.grad.stride(0), table=tgt, src_table=src))
+            ids = feed[s.input_name].data
+            g = buf.grad
+            if (s.buf == "seq" and s.maxlen > 1 and s.hash[0] == L.HASH_NONE and ids.dim() == 2 and ids.is_contiguous()
+                    and g.is_contiguous() and g.shape[1] == s.maxlen * s.dim):
+                # a [B, T] behaviour sequence scattered as B*T independent rows: one sub-warp per ROW instead of
+                # one per sample walking its T rows in sequence (8192 tasks x 50 dependent updates at C4)
+                shard = s.emb.embeddings.opt_state.get("shard")
+                f = K.make_feature(tgt, ids.reshape(-1), g.reshape(-1, s.dim), maxlen=1,
+                                   vocab=shard[2] if shard else s.emb.input_dim)
+                flat.setdefault((batch * s.maxlen, scale), []).append(f)
+                continue
+            feats.append(self._feature(s, feed, g, g.stride(0), table=tgt, src_table=src))
             scales.append(scale)
         # one launch per distinct scale (normally exactly one)
         for sc in sorted(set(scales)):
             K.embed_scatter_add([f for f, s_ in zip(feats, scales) if s_ == sc], batch, sc)
+        for (rows, sc), fs in flat.items():
+            K.embed_scatter_add(fs, rows, sc)
 
     # ---- fusion hooks used by layers ---------------------------------------------------------------
     def lookup_fm(self, x):

@@ -569,6 +569,20 @@ def att_gemm(mode, q2d, ldq, keys2d, key_batch_stride, batch, T, E, n, planes, b
     return out
 
 
+def cin_fold(t0, xk, ldk, rows, m, h, hp, n, w_planes, dy_planes, dt0, dxk, ldx):
+    """dZ = dY W'^T folded onto the factors inside the GEMM epilogue: dt0 [rows, ld0] and dxk [rows, ldx] are
+    accumulated (zero them first; layer 0: dxk is dt0)."""
+    g = L.CinGemm()
+    g.t0, g.ld0, g.xk, g.ldk, g.rows = t0.data_ptr(), t0.stride(0), xk.data_ptr(), ldk, rows
+    g.m, g.h, g.hp, g.n = m, h, hp, n
+    g.w_planes, g.dy_planes = w_planes.data_ptr(), dy_planes.data_ptr()
+    L.check(L.lib().b2ctr_cin_fold(C.byref(g), ptr(dt0), ptr(dxk), ldx, stream()), "cin_fold")
+
+
+def cin_t0_bwd(dt0, ld0, dx, gx, accumulate, nb, m, d):
+    _lib_call("cin_t0_bwd", ptr(dt0), ld0, ptr(dx), gx[0], gx[1], gx[2], int(accumulate), nb, m, d, stream())
+
+
 def cin_unpad_rows(src, m, h, hp):
     n = src.shape[1]
     dst = torch.empty((m * h, n), dtype=torch.float32, device=src.device)
@@ -705,7 +719,7 @@ def dropout(x, rate, seed):
     return y
 
 
-for _n in ("ewise", "cross_vector_fwd", "cross_vector_bwd", "cin_t0", "cin_filter_planes", "cin_gemm", "cin_unpad_rows", "att_gemm",
+for _n in ("ewise", "cross_vector_fwd", "cross_vector_bwd", "cin_t0", "cin_filter_planes", "cin_gemm", "cin_fold", "cin_t0_bwd", "cin_unpad_rows", "att_gemm",
            "cin_outer_fwd", "cin_outer_bwd", "cin_sum_d",
            "cin_expand_grad", "interacting_fwd", "interacting_bwd", "din_att_input_fwd", "din_att_input_bwd",
            "din_pool_fwd", "din_pool_bwd", "seqpool_fwd", "seqpool_bwd", "seqweight", "seqscale", "colstats",
@@ -757,7 +771,7 @@ for _n in ("shard_bucketize", "shard_fill", "shard_gather_rows", "shard_scatter_
     globals()[_n] = _timed(globals()[_n])
 
 
-for _n in ("ewise", "cross_vector_fwd", "cross_vector_bwd", "cin_t0", "cin_filter_planes", "cin_gemm", "cin_unpad_rows", "att_gemm",
+for _n in ("ewise", "cross_vector_fwd", "cross_vector_bwd", "cin_t0", "cin_filter_planes", "cin_gemm", "cin_fold", "cin_t0_bwd", "cin_unpad_rows", "att_gemm",
            "cin_outer_fwd", "cin_outer_bwd", "cin_sum_d",
            "cin_expand_grad", "interacting_fwd", "interacting_bwd", "din_att_input_fwd", "din_att_input_bwd",
            "din_pool_fwd", "din_pool_bwd", "seqpool_fwd", "seqpool_bwd", "seqweight", "seqscale", "colstats",

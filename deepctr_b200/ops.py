@@ -494,6 +494,7 @@ CIN_CHUNK_BYTES = 48 << 20      # outer-product chunk kept well inside the 126 M
 
 
 CIN_FUSED = True              # generate the outer product inside the tcgen05 GEMM producer (b2ctr_cin_gemm)
+CIN_FOLD = True               # ... and fold dZ = dY W^T onto the factors inside the GEMM epilogue (b2ctr_cin_fold)
 CIN_DZ_CHUNK_BYTES = 512 << 20
 
 
@@ -552,9 +553,14 @@ def _cin_fused(x, filters, biases, layer_size, activation, split_half):
         g = grads[0]
         if not g.is_contiguous():
             g = g.contiguous()
-        dx = _empty((B, m * D), x2)
-        K.fill(dx, 0.0)
         gx = (m * D, D, 1)
+        fold = CIN_FOLD and all(hp in (32, 64, 128) for hp in hps)
+        dx = _empty((B, m * D), x2)
+        if fold:
+            dt0 = _empty((rows, ld0), x2)          # gradient of the factor table, all layers accumulate into it
+            K.fill(dt0, 0.0)
+        else:
+            K.fill(dx, 0.0)
         dh = None
         col = out_cols
         for i in range(nl - 1, -1, -1):
@@ -577,21 +583,32 @@ def _cin_fused(x, filters, biases, layer_size, activation, split_half):
             if filters[i].requires_grad:
                 dwp = K.cin_gemm(1, t0, xk, ldk, rows, m, h, hp, size, dzp, split_k=_split_k(kq, size, rows))
                 E.add_grad(filters[i], K.cin_unpad_rows(dwp, m, h, hp).reshape(filters[i].shape))
-            # dZ = dY W'^T in row chunks, folded back onto the two factors
-            dhid = _empty((rows, h), x2) if i > 0 else None
-            chunk = max(256, min(rows, CIN_DZ_CHUNK_BYTES // (4 * kq)) // 256 * 256)
-            dzf = _empty((min(chunk, rows), kq), x2)
-            for r0 in range(0, rows, chunk):
-                nr = min(chunk, rows - r0)
-                K.gemm(dz_[r0:r0 + nr], dz_, c=dzf[:nr], trans_b=True, precision=L.GEMM_BF16X3, m=nr, n=kq, k=size,
-                       b_planes=wplanes[i])
-                b0, nbk = r0 // D, nr // D
-                if i == 0:
-                    K.cin_outer_bwd(dzf, t0, tv0, t0, tv0, dx, gx, True, dx, gx, True, b0, nbk, m, h, D, hp)
-                else:
-                    K.cin_outer_bwd(dzf, t0, tv0, ys[i - 1], xkv, dx, gx, True, dhid, (D * h, 1, h), False, b0, nbk,
-                                    m, h, D, hp)
+            dhid = None
+            if fold:
+                # dZ = dY W'^T exists only as TMEM tiles: the GEMM epilogue folds it onto T0 and X_k
+                if i > 0:
+                    dhid = _empty((rows, h), x2)
+                    K.fill(dhid, 0.0)
+                K.cin_fold(t0, xk, ldk, rows, m, h, hp, size, wplanes[i], dzp, dt0, dt0 if i == 0 else dhid,
+                           ld0 if i == 0 else h)
+            else:
+                # dZ in row chunks, folded back onto the two factors by a second kernel
+                dhid = _empty((rows, h), x2) if i > 0 else None
+                chunk = max(256, min(rows, CIN_DZ_CHUNK_BYTES // (4 * kq)) // 256 * 256)
+                dzf = _empty((min(chunk, rows), kq), x2)
+                for r0 in range(0, rows, chunk):
+                    nr = min(chunk, rows - r0)
+                    K.gemm(dz_[r0:r0 + nr], dz_, c=dzf[:nr], trans_b=True, precision=L.GEMM_BF16X3, m=nr, n=kq, k=size,
+                           b_planes=wplanes[i])
+                    b0, nbk = r0 // D, nr // D
+                    if i == 0:
+                        K.cin_outer_bwd(dzf, t0, tv0, t0, tv0, dx, gx, True, dx, gx, True, b0, nbk, m, h, D, hp)
+                    else:
+                        K.cin_outer_bwd(dzf, t0, tv0, ys[i - 1], xkv, dx, gx, True, dhid, (D * h, 1, h), False, b0, nbk,
+                                        m, h, D, hp)
             dh = dhid
+        if fold:
+            K.cin_t0_bwd(dt0, ld0, dx, gx, False, B, m, D)
         E.add_grad(x, dx.reshape(x.shape))
 
     E.record([res], [x] + list(filters) + list(biases), bwd)

@@ -417,6 +417,17 @@ typedef struct b2ctr_att_gemm {
 B2CTR_API size_t b2ctr_att_gemm_workspace_bytes(const b2ctr_att_gemm_t* g);
 B2CTR_API b2ctr_status_t b2ctr_att_gemm(const b2ctr_att_gemm_t* g, void* workspace, size_t workspace_bytes,
                                        void* stream);
+/* CIN backward, data gradient: dZ = dY W'^T (dy_planes: b2ctr_split_planes of dY [rows, n]; w_planes as in mode 0)
+ * is formed tile by tile in TMEM and FOLDED onto the two factors inside the GEMM epilogue - it is never stored:
+ *   dt0[r, i]  += sum_j dZ[r, i*hp + j] * xk[r, j]        dxk[r, j] += sum_i dZ[r, i*hp + j] * t0[r, i]
+ * Both outputs are accumulated with red.add (zero them first; layer 0 passes dxk = dt0).  hp in {32, 64, 128};
+ * c / ldc / bias / act / mode / split_k of the descriptor are ignored. */
+B2CTR_API b2ctr_status_t b2ctr_cin_fold(const b2ctr_cin_gemm_t* g, float* dt0, float* dxk, int64_t ldx,
+                                       void* stream);
+/* dX0(b,i,d) (+)= dt0[(b*D + d), i] (dX0 given by its three strides). */
+B2CTR_API b2ctr_status_t b2ctr_cin_t0_bwd(const float* dt0, int64_t ld0, float* dx, int64_t gb, int64_t gi,
+                                         int64_t gd, int32_t accumulate, int64_t nb, int32_t m, int32_t d,
+                                         void* stream);
 /* t0[(b*D + d), i] = X0(b,i,d) for i < m, zero for m <= i < ld0 (X0 given by its three strides). */
 B2CTR_API b2ctr_status_t b2ctr_cin_t0(const float* x0, int64_t s0b, int64_t s0i, int64_t s0d, float* t0,
                                      int64_t ld0, int64_t nb, int32_t m, int32_t d, void* stream);

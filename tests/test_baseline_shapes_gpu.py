@@ -62,7 +62,11 @@ def _check_steps(cfg, model, cols, data, lr, nsteps, act="sigmoid", check_update
                 # per duplicate id on the GPU): at these batch sizes an update is only ~100 ulps of its weight
                 ulp = 4.0 * np.finfo(np.float32).eps * float(np.abs(w0).max())
                 err = (np.abs(new[name].numpy() - (w0 - upd)).max() - ulp) / (np.abs(upd).max() + 1e-12)
-                assert err < upd_tol, "step %d weight %s: update mismatch %.3e (relative to max update)" % (step, name, err)
+                # a bias gradient is a column sum over B (x D) rows of relu-masked terms: pre-activations within the
+                # split-bf16 error of zero flip their mask against the fp32 oracle, and the sum cancels to a small
+                # total, so a handful of flipped terms is a visible fraction of it
+                tol = 10 * upd_tol if "bias" in name else upd_tol
+                assert err < tol, "step %d weight %s: update mismatch %.3e (relative to max update)" % (step, name, err)
 
 
 def _logits(model, x):

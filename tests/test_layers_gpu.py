@@ -383,7 +383,8 @@ def test_dropout_mask_is_consistent_between_forward_and_backward(cuda):
     (24, 5, 16, (136, 16), True, "relu"),        # h = 68 -> hp 128 (two k-blocks per i), N = 136 -> two N tiles? (bn 256)
     (300, 26, 16, (128, 128), True, "relu"),     # the C3 layer sizes: K' = 832 / 1664, 2-CTA tiles, ragged last row tile
 ])
-def test_cin_generated_outer_product(cuda, B, F, E_, layer_size, split_half, act):
+@pytest.mark.parametrize("fold", [True, False])
+def test_cin_generated_outer_product(cuda, B, F, E_, layer_size, split_half, act, fold):
     """b2ctr_cin_gemm: the outer product is generated inside the tensor-core GEMM producer (forward and filter
     gradient); checked against the oracle's literal op sequence, all gradients."""
     from deepctr_b200.layers import CIN
@@ -397,12 +398,13 @@ def test_cin_generated_outer_product(cuda, B, F, E_, layer_size, split_half, act
     for w in layer.weights:
         w.set_value(rng.normal(0, 0.2, size=w.shape).astype(np.float32))
     L.reset_launch_count()
-    old = ops.CIN_DZ_CHUNK_BYTES
+    old = ops.CIN_DZ_CHUNK_BYTES, ops.CIN_FOLD
     ops.CIN_DZ_CHUNK_BYTES = 4 * 832 * 1024          # several dZ row chunks at the larger shapes
+    ops.CIN_FOLD = fold                               # dZ folded inside the GEMM epilogue / by a second kernel
     try:
         out, gy, gin, gw = _run(layer, x, rng)
     finally:
-        ops.CIN_DZ_CHUNK_BYTES = old
+        ops.CIN_DZ_CHUNK_BYTES, ops.CIN_FOLD = old
     xt = _t(x)
     fs = [_t(w.value()) for w in layer.filters]
     bs = [_t(w.value()) for w in layer.bias]
@@ -420,7 +422,7 @@ def test_cin_generated_outer_product(cuda, B, F, E_, layer_size, split_half, act
         close(gw["bias%d" % i], bs[i].grad, "bias%d" % i)
 
 
-@pytest.mark.parametrize("B,T,E_,n,act", [(16, 20, 16, 24, "sigmoid"), (40, 50, 64, 80, "relu"), (9, 31, 8, 36, None)])
+@pytest.mark.parametrize("B,T,E_,n,act", [(16, 20, 16, 24, "relu"), (40, 50, 64, 80, "sigmoid"), (9, 31, 8, 36, None)])
 def test_din_first_attention_layer_generated_input(cuda, B, T, E_, n, act):
     """b2ctr_att_gemm: act([q, k, q-k, q*k] W + b) with the [B,T,4E] input generated inside the GEMM producer,
     forward + every gradient against torch."""

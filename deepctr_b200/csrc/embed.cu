@@ -480,13 +480,21 @@ __global__ void __launch_bounds__(256, (SHARD || PLANES) ? 3 : 4)
   const uint64_t pol_keep = l2_policy_evict_last(), pol_stream = l2_policy_evict_first();
   const int64_t nwarps = (int64_t)gridDim.x * (blockDim.x >> 5);
   int64_t b = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
-  // ids: lane l holds features l and l+32
-  int64_t id0 = (b < batch && lane < F) ? uni_id(p, lane, b) : 0;
-  int64_t id1 = (b < batch && lane + 32 < F) ? uni_id(p, lane + 32, b) : 0;
+  // ids: lane l holds features l and l+32.  They are validated against the vocabulary HERE, once per lookup
+  // (an id outside [0, V) becomes -1: zero row, counted), so the row loop only tests a sign.
+  auto checked = [&](int f, int64_t bb) -> int64_t {       // f: this lane's feature (lane or lane + 32)
+    if (bb >= batch || f >= F) return 0;
+    const int64_t id = uni_id(p, f, bb);
+    if (id_in_range(id, p.vocab[f])) return id;
+    note_oob(p.oob);
+    return -1;
+  };
+  int64_t id0 = checked(lane, b);
+  int64_t id1 = checked(lane + 32, b);
   for (; b < batch; b += nwarps) {
     const int64_t bn = b + nwarps;
-    const int64_t nid0 = (bn < batch && lane < F) ? uni_id(p, lane, bn) : 0;        // prefetch
-    const int64_t nid1 = (bn < batch && lane + 32 < F) ? uni_id(p, lane + 32, bn) : 0;
+    const int64_t nid0 = checked(lane, bn);        // prefetch
+    const int64_t nid1 = checked(lane + 32, bn);
     float* xrow = p.x + b * p.ldx;
     float4 s = make_float4(0.f, 0.f, 0.f, 0.f);
     float q = 0.f;
@@ -500,9 +508,8 @@ __global__ void __launch_bounds__(256, (SHARD || PLANES) ? 3 : 4)
         const int64_t idb = __shfl_sync(0xffffffffu, id1, fs & 31);
         const int64_t id = fs < 32 ? ida : idb;
         if (f < F) {
-          if (!id_in_range(id, p.vocab[f])) {               // zero row, counted once per row
+          if (id < 0) {                                     // out of range (see above): zero row
             v[u] = make_float4(0.f, 0.f, 0.f, 0.f);
-            if (chunk == 0) note_oob(p.oob);
           } else if (SHARD) {
             v[u] = ld_peer_f4(shard_row(p.peer_tab, p, f, id, dim) + chunk * 4);
           } else {
@@ -542,8 +549,8 @@ __global__ void __launch_bounds__(256, (SHARD || PLANES) ? 3 : 4)
     if (p.linear != nullptr) {
       float l = 0.f;
       if (p.has_lin) {
-        const bool ok0 = lane < F && id_in_range(id0, p.vocab[lane]);
-        const bool ok1 = lane + 32 < F && id_in_range(id1, p.vocab[lane + 32 < F ? lane + 32 : 0]);
+        const bool ok0 = lane < F && id0 >= 0;
+        const bool ok1 = lane + 32 < F && id1 >= 0;
         if (SHARD) {
           if (ok0) l += ld_peer_f1(shard_row(p.peer_lin, p, lane, id0, 1));
           if (ok1) l += ld_peer_f1(shard_row(p.peer_lin, p, lane + 32, id1, 1));
@@ -591,12 +598,17 @@ __global__ void __launch_bounds__(256, SHARD ? 2 : 3)
   const uint64_t pol_keep = l2_policy_evict_last(), pol_stream = l2_policy_evict_first();
   const int64_t nwarps = (int64_t)gridDim.x * (blockDim.x >> 5);
   int64_t b = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
-  int64_t id0 = (b < batch && lane < F) ? uni_id(p, lane, b) : 0;
-  int64_t id1 = (b < batch && lane + 32 < F) ? uni_id(p, lane + 32, b) : 0;
+  auto checked = [&](int f, int64_t bb) -> int64_t {       // -1: id outside the vocabulary, skipped
+    if (bb >= batch || f >= F) return 0;
+    const int64_t id = uni_id(p, f, bb);
+    return id_in_range(id, p.vocab[f]) ? id : -1;
+  };
+  int64_t id0 = checked(lane, b);
+  int64_t id1 = checked(lane + 32, b);
   for (; b < batch; b += nwarps) {
     const int64_t bn = b + nwarps;
-    const int64_t nid0 = (bn < batch && lane < F) ? uni_id(p, lane, bn) : 0;
-    const int64_t nid1 = (bn < batch && lane + 32 < F) ? uni_id(p, lane + 32, bn) : 0;
+    const int64_t nid0 = checked(lane, bn);
+    const int64_t nid1 = checked(lane + 32, bn);
     const float* xrow = p.x + b * p.ldx;
     const float* dxrow = dx ? dx + b * p.ldx : nullptr;
     const float gfm = dfm ? dfm[b] : 0.f;
@@ -642,7 +654,7 @@ __global__ void __launch_bounds__(256, SHARD ? 2 : 3)
         const int64_t ida = __shfl_sync(0xffffffffu, id0, fs & 31);
         const int64_t idb = __shfl_sync(0xffffffffu, id1, fs & 31);
         const int64_t id = fs < 32 ? ida : idb;
-        if (f < F && id_in_range(id, p.vocab[f])) {
+        if (f < F && id >= 0) {
           float4 r = g[u];
           if (dfm && ((p.fm_mask >> f) & 1ull)) {
             r.x += gfm * (s.x - xv[u].x);
@@ -660,8 +672,8 @@ __global__ void __launch_bounds__(256, SHARD ? 2 : 3)
     }
     if (dlinear && p.has_lin) {
       const float gl = dlinear[b] * lin_scale;
-      const bool ok0 = lane < F && id_in_range(id0, p.vocab[lane]);
-      const bool ok1 = lane + 32 < F && id_in_range(id1, p.vocab[lane + 32 < F ? lane + 32 : 0]);
+      const bool ok0 = lane < F && id0 >= 0;
+      const bool ok1 = lane + 32 < F && id1 >= 0;
       if (SHARD) {
         if (ok0) red_peer_f1(shard_row(p.peer_lin, p, lane, id0, 1), gl);
         if (ok1) red_peer_f1(shard_row(p.peer_lin, p, lane + 32, id1, 1), gl);

@@ -897,6 +897,8 @@ class Feeder(object):
             width = int(np.prod(tail)) if tail else 1
             self._meta[name] = (width, spec.dtype in ("float32", "float64", "float16"), spec.dtype == "int64", tail)
         self._pinned = {}
+        self._carrays = {}
+        self._plan = None
         self._views = {}
         self._copied_ev = {}
         self._consumed_ev = {}
@@ -985,8 +987,71 @@ class Feeder(object):
         self.h2d_bytes += host.numel() * host.element_size()
         return dev
 
+    # ---- steady-state path -------------------------------------------------------------------------------
+    # fit() feeds thousands of batches of identical structure (one contiguous numpy array per feature, fixed
+    # dtypes).  After a batch went through the general path below, its structure is remembered; the next batches
+    # only have their array pointers collected (~2 us per input) before the native pack + the H2D copies: the
+    # per-step Python cost of the input pipeline must stay well under the ~1.2 ms training step it feeds.
+    def _feed_fast(self, xd):
+        plan = getattr(self, "_plan", None)
+        if plan is None:
+            return None
+        b = -1
+        ptrs = {}
+        for key, np_dt, items, _ in plan:
+            col = []
+            for name, w in items:
+                a = xd.get(name)
+                if type(a) is not np.ndarray or a.dtype != np_dt or not a.flags.c_contiguous:
+                    return None
+                if b < 0:
+                    b = a.shape[0]
+                if a.shape[0] != b or not ((a.ndim == 1 and w == 1) or (a.ndim == 2 and a.shape[1] == w)):
+                    return None
+                col.append(a.__array_interface__["data"][0])
+            ptrs[key] = col
+        slot = (getattr(self, "slot", -1) + 1) % self._RING
+        for key, np_dt, items, names in plan:          # every view of the slot this batch will land in must exist
+            if (slot, key, b, names) not in self._views:
+                return None
+        self._next_slot()
+        feed = {}
+        th_dt = {"i32": torch.int32, "i64": torch.int64, "f32": torch.float32}
+        for key, np_dt, items, names in plan:
+            total = sum(w for _, w in items)
+            stage, dbuf = self._stage(key, (b * total,), th_dt[key])
+            ck = (key, b)
+            arrs = self._carrays.get(ck)
+            if arrs is None:
+                n = len(items)
+                src, nbytes, offs = (C.c_void_p * n)(), (C.c_int64 * n)(), (C.c_int64 * n)()
+                off, isz = 0, np.dtype(np_dt).itemsize
+                for i, (_, w) in enumerate(items):
+                    nbytes[i], offs[i] = b * w * isz, off * isz
+                    off += b * w
+                arrs = self._carrays[ck] = (src, nbytes, offs, n)
+            src, nbytes, offs, n = arrs
+            for i, pv in enumerate(ptrs[key]):
+                src[i] = pv
+            L.check(L.lib().b2ctr_host_pack(src, nbytes, offs, n, C.c_void_p(stage.data_ptr()), _pack_threads()),
+                    "host_pack")
+            pack = self._upload(stage, dbuf)
+            cached = self._views[(self.slot, key, b, names)]
+            if key == "f32":
+                if len(items) > 1:
+                    _, pbuf = self._stage("f32pack", (b, total), torch.float32)
+                    K.pack_rows(pack, [w for _, w in items], b, out=pbuf)
+                for v in cached.values():          # per-step state of a reused Var
+                    v.grad = None
+                    v.planes = None
+            feed.update(cached)
+        return feed
+
     def feed(self, x, batch_slice=None):
         xd = self._as_dict(x)
+        fast = self._feed_fast(xd)
+        if fast is not None:
+            return fast
         self._next_slot()
         groups = {"i32": [], "i64": [], "f32": []}
         arrays = {}
@@ -1078,6 +1143,18 @@ class Feeder(object):
                     v.grad = None
                     v.planes = None
             feed.update(cached)
+        # remember the structure of an all-host batch for the steady-state path
+        if not arrays and not self.host_hash:
+            plan = []
+            for key, items in groups.items():
+                if items and all(type(a) is np.ndarray and a.dtype == np_dt[key] and a.flags.c_contiguous
+                                 for _, a, _ in items):
+                    plan.append((key, np.dtype(np_dt[key]), [(name, w) for name, _, w in items],
+                                 tuple(name for name, _, _ in items)))
+                elif items:
+                    plan = None
+                    break
+            self._plan = plan or None
         # device-resident inputs: float columns that are views of one [B, nd] buffer form a dense pack
         packs = {}
         for name, (_, a) in arrays.items():

@@ -45,6 +45,12 @@ def _split_k(m_out, n_out, kred):
     """wgrad-style GEMMs reduce over the batch: one K slice per CTA pair (74 pairs of SMs, 256 x 256 tiles)."""
     if kred < 4096:
         return 1
+    if n_out <= 8:
+        # skinny wgrad (the [*, 1] projections, CrossNet's w): an HBM stream over the batch handled by
+        # skinny_tn_kernel, one CTA per (64-column block, K slice) - slices of ~256 rows, up to 4 CTAs per SM
+        # (64 slices of 1024 rows left 57 % of the SMs idle: 86 us for a 16 MB read, ncu r2_launches_c2.csv)
+        blocks = (m_out + 63) // 64
+        return int(max(1, min(592 // blocks, kred // 256)))
     tiles = ((m_out + 255) // 256) * ((n_out + 255) // 256)
     return int(max(1, min(74 // tiles if tiles <= 74 else 1, kred // 1024)))
 

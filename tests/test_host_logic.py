@@ -192,7 +192,8 @@ def test_dense_gemm_policy_helpers():
     from deepctr_b200 import ops, kernels as K
     assert ops._split_k(845, 256, 65536) == 18            # 4 pair tiles x 18 K slices = 72 of 74 SM pairs
     assert ops._split_k(256, 128, 65536) == 64            # one tile: capped by K / 1024
-    assert ops._split_k(64, 1, 65536) == 64
+    assert ops._split_k(64, 1, 65536) == 256               # skinny wgrad: ~256-row slices, up to 592 CTAs
+    assert ops._split_k(845, 1, 65536) == 42               # 14 column blocks x 42 slices = 588 CTAs
     assert ops._split_k(845, 256, 2048) == 1              # short reductions are not split
     assert ops._split_k(30000, 30000, 1 << 20) == 1       # more tiles than SM pairs
     assert K.planes_fusable(65536, 256) and K.planes_fusable(65536, 128) and K.planes_fusable(65536, 64)

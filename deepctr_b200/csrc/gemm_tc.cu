@@ -379,6 +379,7 @@ struct PlaneArgs {
   int cin_m, cin_h, cin_hp, cin_on;
   // FOLD epilogue (CIN backward): dT0 [rows, cin_ld0] and dXk [rows, fold_ldx], both accumulated with red.add
   float* fold_dt0; float* fold_dxk; int64_t fold_ldx;
+  int gen_groups;     // generating producers: 2 = two groups of 128 threads alternate stages, 1 = all 256 share every stage
 };
 
 // dst planes [rows_pad, k_pad] <- src(r, k) = p[r*sr + k*sk]; zero outside [rows, k).
@@ -771,96 +772,90 @@ __device__ __forceinline__ void split_pair(float v0, float v1, uint32_t& h, uint
   const __nv_bfloat162 ll = __floats2bfloat162_rn(v0 - h0, v1 - h1);
   l = *reinterpret_cast<const uint32_t*>(&ll);
 }
-// ---- generated A operand ------------------------------------------------------------------------------------
-// A stage of the generated operand is 128 "rows" x 64 columns (K-major: rows = M, columns = one k-block; MN-major:
-// rows = (atom, k-row), columns = the atom's 64 M values).  The 256 producer threads cover it as (row, QUAD of 4
-// columns): 16 consecutive threads read one 256-byte row segment of the second factor with ONE fully coalesced
-// 16-byte load each (the first layout of this producer - a thread per half row - touched 16 cache lines per load
-// instruction and ran the L1 out of tag bandwidth: ncu, profiles/r2_cin_before.txt), multiply, split into bf16
-// hi/lo and store 8 bytes per plane into the 128-byte-swizzled row.  8 passes of 16 rows per stage.
-struct GenTask {
-  int i, j;       // CIN: factor index pair of this thread's quad;  DIN: (segment, offset inside the segment)
-};
-__device__ __forceinline__ void store_quad(float v0, float v1, float v2, float v3, unsigned char* hi_row,
-                                           unsigned char* lo_row, int off) {
-  uint32_t h0, l0, h1, l1;
-  split_pair(v0, v1, h0, l0);
-  split_pair(v2, v3, h1, l1);
-  *reinterpret_cast<uint2*>(hi_row + off) = make_uint2(h0, h1);
-  *reinterpret_cast<uint2*>(lo_row + off) = make_uint2(l0, l1);
+__device__ __forceinline__ void store_chunk(const float (&v)[8], unsigned char* hi_row, unsigned char* lo_row, int off) {
+  uint32_t h[4], l[4];
+#pragma unroll
+  for (int e = 0; e < 4; ++e) split_pair(v[2 * e], v[2 * e + 1], h[e], l[e]);
+  *reinterpret_cast<uint4*>(hi_row + off) = make_uint4(h[0], h[1], h[2], h[3]);
+  *reinterpret_cast<uint4*>(lo_row + off) = make_uint4(l[0], l[1], l[2], l[3]);
 }
-// CIN: A[r, i*hp + j] = t0[r, i] * xk[r, j] (j < h, i < m)
-__device__ __forceinline__ float4 cin_quad(const PlaneArgs& g, int64_t r, GenTask t) {
-  float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-  if (r < g.cin_rows && t.i < g.cin_m && t.j < g.cin_h) {
-    const float a = __ldg(g.cin_t0 + r * g.cin_ld0 + t.i);
-    // h % 4 == 0, or the rows are padded to hp: a quad starting below h lies inside the row
-    const float4 x = __ldg(reinterpret_cast<const float4*>(g.cin_xk + r * g.cin_ldk + t.j));
-    v = make_float4(a * x.x, a * x.y, a * x.z, a * x.w);
-    if (t.j + 1 >= g.cin_h) v.y = 0.f;
-    if (t.j + 2 >= g.cin_h) v.z = 0.f;
-    if (t.j + 3 >= g.cin_h) v.w = 0.f;
+
+// Generated A operand, CIN: one producer thread = half a row r of the outer product per stage: 32 consecutive
+// q = i*hp + j starting at q0 (a multiple of 32; hp is 32 or a multiple of 64, so 8-element chunks never straddle
+// an i), split into bf16 hi/lo and stored as four 16-byte chunks [c0, c0+4) of the 128-byte-swizzled row `rr`.
+__device__ __forceinline__ void cin_generate_half(const PlaneArgs& g, int64_t r, int q0, unsigned char* hi_row,
+                                                  unsigned char* lo_row, int rr, int c0) {
+  const bool row_ok = r < g.cin_rows;
+  const float* xk = g.cin_xk + r * g.cin_ldk;
+  const float* t0 = g.cin_t0 + r * g.cin_ld0;
+  const int hp = g.cin_hp, h = g.cin_h;
+  int i = q0 / hp, j = q0 - i * hp;
+  float a = (row_ok && i < g.cin_m) ? __ldg(t0 + i) : 0.f;
+  float4 x[8];
+#pragma unroll
+  for (int c = 0; c < 4; ++c) {          // all eight 16-byte loads first (independent of a)
+    const int jj = j + 8 * c >= hp ? j + 8 * c - hp : j + 8 * c;
+    // h % 4 == 0 or the rows are padded to hp: a quad starting below h is inside the row
+    x[2 * c] = (row_ok && jj < h) ? __ldg(reinterpret_cast<const float4*>(xk + jj)) : make_float4(0.f, 0.f, 0.f, 0.f);
+    x[2 * c + 1] = (row_ok && jj + 4 < h) ? __ldg(reinterpret_cast<const float4*>(xk + jj) + 1)
+                                          : make_float4(0.f, 0.f, 0.f, 0.f);
   }
-  return v;
-}
-// DIN (deepctr/layers/core.py:96-101): row r = (b, t), A[r, :] = [ q_b , k_bt , q_b - k_bt , q_b * k_bt ]
-// cin_t0 = queries [B, ld0], cin_xk = keys (sample stride cin_ldk, row stride E), cin_m = T, cin_h = E (E % 4 == 0).
-__device__ __forceinline__ float4 att_quad(const PlaneArgs& g, int64_t r, GenTask t) {
-  float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-  if (r < g.cin_rows && t.i < 4) {
-    const uint32_t bu = (uint32_t)r / (uint32_t)g.cin_m;       // rows < 2^31 (checked on the host): 32-bit division
-    const int64_t b = bu;
-    const int tt = (int)((uint32_t)r - bu * (uint32_t)g.cin_m);
-    float4 q = v, k = v;
-    if (t.i != 1) q = __ldg(reinterpret_cast<const float4*>(g.cin_t0 + b * g.cin_ld0 + t.j));
-    if (t.i != 0) k = __ldg(reinterpret_cast<const float4*>(g.cin_xk + b * g.cin_ldk + (int64_t)tt * g.cin_h + t.j));
-    if (t.i == 0) v = q;
-    else if (t.i == 1) v = k;
-    else if (t.i == 2) v = make_float4(__fsub_rn(q.x, k.x), __fsub_rn(q.y, k.y), __fsub_rn(q.z, k.z), __fsub_rn(q.w, k.w));
-    else v = make_float4(__fmul_rn(q.x, k.x), __fmul_rn(q.y, k.y), __fmul_rn(q.z, k.z), __fmul_rn(q.w, k.w));
-  }
-  return v;
-}
-__device__ __forceinline__ GenTask gen_task(const PlaneArgs& g, int64_t col) {
-  GenTask t;
-  const int period = g.cin_on == 2 ? g.cin_h : g.cin_hp;      // DIN: segment width E;  CIN: padded h
-  t.i = (int)((uint32_t)col / (uint32_t)period);              // generated width < 2^31
-  t.j = (int)((uint32_t)col - (uint32_t)t.i * (uint32_t)period);
-  return t;
-}
-// one stage: `tid` in [0, 256); m0 / k0 = first M / K index of the stage; stp = stage base (hi plane), lo at +A_PLANE
-__device__ __forceinline__ void generate_stage(const PlaneArgs& g, int tid, int64_t m0, int64_t k0, unsigned char* stp,
-                                               int a_plane) {
-  const int quad = tid & 15, r16 = tid >> 4;
-  const int qoff = ((quad >> 1) << 4), qlo = (quad & 1) * 8;
-  float4 v[8];
-  if (g.a_mn) {      // rows = (atom, k-row): M = generated column index, K = r
-    const GenTask t0 = gen_task(g, m0 + quad * 4), t1 = gen_task(g, m0 + 64 + quad * 4);
 #pragma unroll
-    for (int p = 0; p < 8; ++p) {
-      const int kr = (p & 3) * 16 + r16;
-      v[p] = g.cin_on == 2 ? att_quad(g, k0 + kr, p < 4 ? t0 : t1) : cin_quad(g, k0 + kr, p < 4 ? t0 : t1);
+  for (int c = 0; c < 4; ++c) {
+    float v[8] = {a * x[2 * c].x, a * x[2 * c].y, a * x[2 * c].z, a * x[2 * c].w,
+                  a * x[2 * c + 1].x, a * x[2 * c + 1].y, a * x[2 * c + 1].z, a * x[2 * c + 1].w};
+    if (h & 7) {                         // ragged h: zero the tail of the last chunk
+#pragma unroll
+      for (int e = 0; e < 8; ++e)
+        if (j + e >= h) v[e] = 0.f;
     }
-#pragma unroll
-    for (int p = 0; p < 8; ++p) {
-      const int kr = (p & 3) * 16 + r16;
-      unsigned char* row = stp + (p >> 2) * 8192 + kr * 128;
-      store_quad(v[p].x, v[p].y, v[p].z, v[p].w, row, row + a_plane, (qoff ^ ((kr & 7) << 4)) + qlo);
-    }
-  } else {           // rows = M = r, columns = one k-block of the generated index
-    const GenTask t = gen_task(g, k0 + quad * 4);
-#pragma unroll
-    for (int p = 0; p < 8; ++p) {
-      const int rr = p * 16 + r16;
-      v[p] = g.cin_on == 2 ? att_quad(g, m0 + rr, t) : cin_quad(g, m0 + rr, t);
-    }
-#pragma unroll
-    for (int p = 0; p < 8; ++p) {
-      const int rr = p * 16 + r16;
-      unsigned char* row = stp + rr * 128;
-      store_quad(v[p].x, v[p].y, v[p].z, v[p].w, row, row + a_plane, (qoff ^ ((rr & 7) << 4)) + qlo);
+    store_chunk(v, hi_row, lo_row, ((c0 + c) ^ (rr & 7)) << 4);
+    j += 8;
+    if (j >= hp) {                       // next i (only when hp == 32: two i per 64-deep k-block)
+      j = 0;
+      ++i;
+      a = (row_ok && i < g.cin_m) ? __ldg(t0 + i) : 0.f;
     }
   }
+}
+
+// DIN local-activation-unit input (deepctr/layers/core.py:96-101), generated the same way: row r = (b, t),
+//   A[r, :] = [ q_b , k_bt , q_b - k_bt , q_b * k_bt ]   (4 segments of E columns; E % 8 == 0)
+// cin_t0 = queries [B, ld0], cin_xk = keys (sample stride cin_ldk, row stride E), cin_m = T, cin_h = E.
+__device__ __forceinline__ void att_generate_half(const PlaneArgs& g, int64_t r, int col0, unsigned char* hi_row,
+                                                  unsigned char* lo_row, int rr, int c0) {
+  const int T = g.cin_m, E = g.cin_h;
+  const bool row_ok = r < g.cin_rows;
+  const uint32_t bu = row_ok ? (uint32_t)r / (uint32_t)T : 0u;      // rows < 2^31 (checked on the host)
+  const int64_t b = bu;
+  const int t = row_ok ? (int)((uint32_t)r - bu * (uint32_t)T) : 0;
+  const float* q = g.cin_t0 + b * g.cin_ld0;
+  const float* k = g.cin_xk + b * g.cin_ldk + (int64_t)t * E;
+#pragma unroll
+  for (int c = 0; c < 4; ++c) {
+    const int col = col0 + 8 * c;
+    const int seg = col / E, e = col - seg * E;
+    float v[8];
+    if (row_ok && seg < 4) {
+      float4 a0 = make_float4(0.f, 0.f, 0.f, 0.f), a1 = a0, b0 = a0, b1 = a0;
+      if (seg != 1) { a0 = __ldg(reinterpret_cast<const float4*>(q + e)); a1 = __ldg(reinterpret_cast<const float4*>(q + e) + 1); }
+      if (seg != 0) { b0 = __ldg(reinterpret_cast<const float4*>(k + e)); b1 = __ldg(reinterpret_cast<const float4*>(k + e) + 1); }
+      const float qa[8] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w};
+      const float ka[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
+#pragma unroll
+      for (int jx = 0; jx < 8; ++jx)
+        v[jx] = seg == 0 ? qa[jx] : seg == 1 ? ka[jx] : seg == 2 ? __fsub_rn(qa[jx], ka[jx]) : __fmul_rn(qa[jx], ka[jx]);
+    } else {
+#pragma unroll
+      for (int jx = 0; jx < 8; ++jx) v[jx] = 0.f;
+    }
+    store_chunk(v, hi_row, lo_row, ((c0 + c) ^ (rr & 7)) << 4);
+  }
+}
+__device__ __forceinline__ void generate_half(const PlaneArgs& g, int64_t r, int q0, unsigned char* hi_row,
+                                              unsigned char* lo_row, int rr, int c0) {
+  if (g.cin_on == 2) att_generate_half(g, r, q0, hi_row, lo_row, rr, c0);
+  else cin_generate_half(g, r, q0, hi_row, lo_row, rr, c0);
 }
 
 // generated-operand kernels run 8 producer warps (two threads per generated row), the others 4
@@ -896,7 +891,8 @@ __global__ void __launch_bounds__(WsLayout<CIN>::kThreads, 1)
     for (int s = 0; s < STAGES; ++s) {
       // cp.async producers: one deferred arrival per producer thread of THIS CTA; TMA: one arrive.expect_tx
       // CIN: the B planes arrive by TMA (1 arrive.expect_tx) + one arrival per generating thread
-      mbar_init(&full_bar[s], CIN ? 1 + WsLayout<CIN>::kProducers * 32 : (TMA ? 1 : kWsProducers * 32));
+      // generated A: one group of 128 threads per stage + the TMA expect_tx of the B planes
+      mbar_init(&full_bar[s], CIN ? 1 + (g.gen_groups == 2 ? 128 : 256) : (TMA ? 1 : kWsProducers * 32));
       mbar_init(&peer_full[s], 1);                    // leader only: the peer CTA's half of the stage landed
       mbar_init(&empty_bar[s], 1);
     }
@@ -948,10 +944,15 @@ __global__ void __launch_bounds__(WsLayout<CIN>::kThreads, 1)
 
   constexpr int kMmaWarp = WsLayout<CIN>::kMmaWarp;
   if (CIN && warp >= kWsEpilogueWarps && warp < kMmaWarp) {
-    // ------------------------------------------------------------------------------ CIN producers
-    // B (filter / dY planes) by TMA from thread 0; A generated in place by all 128 producer threads.
+    // ------------------------------------------------------------------------------ generating producers
+    // 8 warps in TWO GROUPS of 128 threads; group g owns the stages with (stage counter & 1) == g and generates a
+    // whole row (64 columns) per thread for them.  Two stages are therefore in production at any time: while one
+    // group waits for its global loads (the producer is load-latency-bound: ncu source page, FMUL on the loaded
+    // operands holds the stall samples), the other one multiplies / splits / stores.  B (filter / dY planes)
+    // arrives by TMA, issued by thread 0 of the group that owns the stage.
     const int tid = threadIdx.x - kWsEpilogueWarps * 32;
-    if (tid == 0) { tma_prefetch_desc(&tm_bh); tma_prefetch_desc(&tm_bl); }
+    const int grp = tid >> 7, t128 = tid & 127;
+    if (t128 == 0) { tma_prefetch_desc(&tm_bh); tma_prefetch_desc(&tm_bl); }
     uint32_t it = 0;
     for (int64_t tile = cluster_id; tile < w.ntiles; tile += nclusters) {
       int64_t mt, nt, kbeg;
@@ -960,11 +961,13 @@ __global__ void __launch_bounds__(WsLayout<CIN>::kThreads, 1)
       const int64_t m0 = (mt * NCTA + cta_rank) * kTM;
       const int32_t n0 = (int32_t)(nt * BN + (int64_t)cta_rank * BNH);
       for (int kb = 0; kb < nkb; ++kb, ++it) {
+        const bool two = g.gen_groups == 2;
+        if (two && (int)(it & 1) != grp) continue;
         const int s = it % STAGES;
         mbar_wait(&empty_bar[s], ((it / STAGES) & 1) ^ 1);
         unsigned char* stp = tiles + (size_t)s * STAGE;
         const int64_t k0 = kbeg + (int64_t)kb * kTK;
-        if (tid == 0) {
+        if (two ? t128 == 0 : tid == 0) {
           uint64_t* bar = &full_bar[s];
           mbar_expect_tx(bar, (uint32_t)(2 * B_PLANE));
           const uint32_t st = smem_u32(stp);
@@ -979,7 +982,28 @@ __global__ void __launch_bounds__(WsLayout<CIN>::kThreads, 1)
             tma_load_2d(st + 2 * A_PLANE + B_PLANE, &tm_bl, (int32_t)k0, n0, bar);
           }
         }
-        generate_stage(g, tid, m0, k0, stp, A_PLANE);
+        if (two) {
+          if (g.a_mn) {      // A^T: M = q (two 64-wide atoms), K = r: thread -> (atom, k-row)
+            const int atom = t128 >> 6, rr = t128 & 63;
+            unsigned char* row = stp + atom * 8192 + rr * 128;
+            generate_half(g, k0 + rr, (int)(m0 + atom * 64), row, row + A_PLANE, rr, 0);
+            generate_half(g, k0 + rr, (int)(m0 + atom * 64 + 32), row, row + A_PLANE, rr, 4);
+          } else {           // A: M = r, K = q: thread -> row
+            unsigned char* row = stp + t128 * 128;
+            generate_half(g, m0 + t128, (int)k0, row, row + A_PLANE, t128, 0);
+            generate_half(g, m0 + t128, (int)(k0 + 32), row, row + A_PLANE, t128, 4);
+          }
+        } else {
+          const int half = tid & 1;           // two threads per generated row: 32 of its 64 columns each
+          if (g.a_mn) {
+            const int atom = tid >> 7, rr = (tid & 127) >> 1;
+            generate_half(g, k0 + rr, (int)(m0 + atom * 64 + half * 32), stp + atom * 8192 + rr * 128,
+                          stp + A_PLANE + atom * 8192 + rr * 128, rr, half * 4);
+          } else {
+            const int rr = tid >> 1;
+            generate_half(g, m0 + rr, (int)(k0 + half * 32), stp + rr * 128, stp + A_PLANE + rr * 128, rr, half * 4);
+          }
+        }
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
         mbar_arrive(&full_bar[s]);
       }
@@ -1536,7 +1560,7 @@ static b2ctr_status_t gemm_planes(const b2ctr_gemm_t* g, void* workspace, size_t
   pa.k_per_split = ceil_div(ceil_div(kp, splits), kTK) * kTK;
   pa.alpha = g->alpha; pa.act = g->act; pa.accumulate = g->accumulate; pa.splits = splits;
   pa.cin_on = 0; pa.cin_t0 = pa.cin_xk = nullptr; pa.cin_ld0 = pa.cin_ldk = pa.cin_rows = 0; pa.cin_m = pa.cin_h = pa.cin_hp = 0;
-  pa.fold_dt0 = pa.fold_dxk = nullptr; pa.fold_ldx = 0;
+  pa.fold_dt0 = pa.fold_dxk = nullptr; pa.fold_ldx = 0; pa.gen_groups = 0;
   cudaError_t e;
   const bool short_k = pa.k_per_split <= 4 * kTK;
   if (ws_kernel) {
@@ -1652,6 +1676,11 @@ static b2ctr_status_t gen_gemm(const GenSpec& sp, int mode, int64_t n, const voi
   pa.cin_on = sp.kind; pa.cin_t0 = sp.p0; pa.cin_xk = sp.p1; pa.cin_ld0 = sp.ld0; pa.cin_ldk = sp.ld1;
   pa.cin_rows = sp.rows; pa.cin_m = sp.m; pa.cin_h = sp.h; pa.cin_hp = sp.hp;
   pa.fold_dt0 = pa.fold_dxk = nullptr; pa.fold_ldx = 0;
+  {
+    static int groups = -1;
+    if (groups < 0) { const char* ev = getenv("B2CTR_GEN_GROUPS"); groups = ev ? atoi(ev) : 2; }
+    pa.gen_groups = groups == 1 ? 1 : 2;
+  }
   pa.b_mn = 1;      // both B operands are row-major matrices whose reduction dim is their row index
   pa.c = c; pa.bias = bias; pa.ws = (float*)workspace; pa.ldc = ldc;
   pa.alpha = 1.f; pa.act = act; pa.accumulate = 0; pa.splits = splits;
@@ -1748,7 +1777,7 @@ b2ctr_status_t cin_fold(const b2ctr_cin_gemm_t* g, float* dt0, float* dxk, int64
   pa.k_per_split = pa.k_pad; pa.alpha = 1.f; pa.act = 0; pa.accumulate = 0; pa.splits = 1;
   pa.cin_on = 0; pa.cin_t0 = g->t0; pa.cin_xk = g->xk; pa.cin_ld0 = g->ld0; pa.cin_ldk = g->ldk; pa.cin_rows = g->rows;
   pa.cin_m = g->m; pa.cin_h = g->h; pa.cin_hp = g->hp;
-  pa.fold_dt0 = dt0; pa.fold_dxk = dxk; pa.fold_ldx = ldx;
+  pa.fold_dt0 = dt0; pa.fold_dxk = dxk; pa.fold_ldx = ldx; pa.gen_groups = 0;
   constexpr int bn = 128;
   const int ncta = g->rows > kTM ? 2 : 1;
   WsArgs wa;

@@ -152,6 +152,8 @@ __device__ __forceinline__ float4 vmuls(float4 a, float s) {
   return make_float4(__fmul_rn(a.x, s), __fmul_rn(a.y, s), __fmul_rn(a.z, s), __fmul_rn(a.w, s));
 }
 __device__ __forceinline__ float vmuls(float a, float s) { return __fmul_rn(a, s); }
+__device__ __forceinline__ bool vnonzero(float4 a) { return a.x != 0.f || a.y != 0.f || a.z != 0.f || a.w != 0.f; }
+__device__ __forceinline__ bool vnonzero(float a) { return a != 0.f; }
 __device__ __forceinline__ float4 vdivs(float4 a, float s) {
   return make_float4(__fdiv_rn(a.x, s), __fdiv_rn(a.y, s), __fdiv_rn(a.z, s), __fdiv_rn(a.w, s));
 }
@@ -307,6 +309,7 @@ __global__ void __launch_bounds__(256)
   using V = typename VecT<VEC>::T;
   constexpr int kGroups = 256 / G;
   const int lane = threadIdx.x % G;
+  const unsigned gmask = G >= 32 ? 0xffffffffu : (((1u << (G & 31)) - 1u) << ((threadIdx.x & 31) / G * G));
   const int64_t ntasks = batch * fb.nfeat;
   for (int64_t task = (int64_t)blockIdx.x * kGroups + threadIdx.x / G; task < ntasks;
        task += (int64_t)gridDim.x * kGroups) {
@@ -320,6 +323,11 @@ __global__ void __launch_bounds__(256)
       for (int t = 0; t < T; ++t) {
         const int64_t id = lookup_id(ft, ibase + t);
         if (!id_in_range(id, ft.vocab)) continue;          // never write outside the table
+        // an all-zero gradient row (every masked position of a behaviour sequence: half of a padded batch,
+        // all of them aimed at row 0) changes nothing: skip its atomics
+        bool nz = false;
+        for (int e = lane * VEC; e < dim; e += G * VEC) nz |= vnonzero(vload(gout + (int64_t)t * dim + e, (V*)nullptr));
+        if (__ballot_sync(gmask, nz) == 0u) continue;
         float* row = ft.table + id * dim;
         for (int e = lane * VEC; e < dim; e += G * VEC)
           vred(row + e, vmuls(vload(gout + (int64_t)t * dim + e, (V*)nullptr), scale));

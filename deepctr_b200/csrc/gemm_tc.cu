@@ -1678,8 +1678,10 @@ static b2ctr_status_t gen_gemm(const GenSpec& sp, int mode, int64_t n, const voi
   pa.fold_dt0 = pa.fold_dxk = nullptr; pa.fold_ldx = 0;
   {
     static int groups = -1;
-    if (groups < 0) { const char* ev = getenv("B2CTR_GEN_GROUPS"); groups = ev ? atoi(ev) : 2; }
-    pa.gen_groups = groups == 1 ? 1 : 2;
+    if (groups < 0) { const char* ev = getenv("B2CTR_GEN_GROUPS"); groups = ev ? atoi(ev) : 0; }
+    // measured (profiles/README.md): the CIN generator is faster with all 256 threads on every stage (C3 8.02 vs
+    // 8.32 ms), the attention generator with two groups alternating stages (C4 3.55 vs 3.59 ms)
+    pa.gen_groups = groups == 1 || groups == 2 ? groups : (sp.kind == 1 ? 1 : 2);
   }
   pa.b_mn = 1;      // both B operands are row-major matrices whose reduction dim is their row index
   pa.c = c; pa.bias = bias; pa.ws = (float*)workspace; pa.ldc = ldc;

@@ -989,7 +989,7 @@ class Model(object):
         # CUDA-graph replay of the training step ('auto': on whenever the step is capturable)
         from . import ops as _ops
         self.step_graph = step_graph if os.environ.get("B2CTR_STEP_GRAPH", "1") != "0" else "off"
-        self._step_graphs, self._graph_pool, self._eager_steps = {}, None, 0
+        self._step_graphs, self._graph_pool, self._eager_steps, self._eager_shapes = {}, None, 0, {}
         self.replayed_launches = 0             # kernels executed through graph replays (bench accounting)
         self._uncapturable0 = _ops.UNCAPTURABLE
         # multi-GPU (one process per GPU): dense weights data-parallel, fast-path tables row-sharded
@@ -1121,7 +1121,11 @@ class Model(object):
             if train and self._graph_eligible():
                 key = self._graph_key(feed, labels)
                 ent = self._step_graphs.get(key)
-                if ent is None and self._eager_steps >= 2 and len(self._step_graphs) < 8:
+                shapes = tuple(it[2] for it in key[0])
+                if (ent is None and self._eager_steps >= 2 and self._eager_shapes.get(shapes, 0) >= 1
+                        and len(self._step_graphs) < 8):
+                    # (a batch shape is captured only after it ran eagerly once: first-use work - per-shape launch
+                    # plans, lazily created state - includes host-synchronous copies that a capture cannot hold)
                     ent = self._capture_step(key, feed, labels)
                 if ent is not None:
                     self.optimizer.iterations += 1
@@ -1131,6 +1135,9 @@ class Model(object):
             out = self._loss_step_impl(feed, labels, train)
             if train:
                 self._eager_steps += 1
+                shapes = tuple(tuple(v.data.shape) if isinstance(v, Var) else tuple(v.shape)
+                               for _, v in sorted(feed.items()) if (v.data if isinstance(v, Var) else v) is not None)
+                self._eager_shapes[shapes] = self._eager_shapes.get(shapes, 0) + 1
             return out
         finally:
             self._feeder.consumed(slot)

@@ -819,6 +819,57 @@ __device__ __forceinline__ void cin_generate_half(const PlaneArgs& g, int64_t r,
   }
 }
 
+// The same half row in two steps, so that the producer loop can issue the global loads of k-block kb + 1 before it
+// multiplies / splits / stores k-block kb (the generator is load-latency-bound: its operands come from L2).
+struct CinRegs {
+  float a;
+  float4 x[8];
+};
+__device__ __forceinline__ void cin_load_half(const PlaneArgs& g, int64_t r, int q0, CinRegs& o) {
+  const bool row_ok = r < g.cin_rows;
+  const float* xk = g.cin_xk + r * g.cin_ldk;
+  const int hp = g.cin_hp, h = g.cin_h;
+  const int i = q0 / hp, j = q0 - i * hp;          // hp is 32 or a multiple of 64: the 32 columns share one i
+  o.a = (row_ok && i < g.cin_m) ? __ldg(g.cin_t0 + r * g.cin_ld0 + i) : 0.f;
+#pragma unroll
+  for (int c = 0; c < 4; ++c) {
+    const int jj = j + 8 * c;
+    o.x[2 * c] = (row_ok && jj < h) ? __ldg(reinterpret_cast<const float4*>(xk + jj)) : make_float4(0.f, 0.f, 0.f, 0.f);
+    o.x[2 * c + 1] = (row_ok && jj + 4 < h) ? __ldg(reinterpret_cast<const float4*>(xk + jj) + 1)
+                                            : make_float4(0.f, 0.f, 0.f, 0.f);
+  }
+}
+// multiply / split / store the half row held in `io` (k-block kb) and refill each register pair with the operands
+// of k-block kb + 1 as soon as it has been consumed: a rolling prefetch that costs no extra registers.
+__device__ __forceinline__ void cin_emit_half(const PlaneArgs& g, CinRegs& io, int q0, unsigned char* hi_row,
+                                              unsigned char* lo_row, int rr, int c0, bool has_next, int64_t r_next,
+                                              int q0_next) {
+  const int hp = g.cin_hp, h = g.cin_h;
+  const int j = q0 - (q0 / hp) * hp;
+  const float a = io.a;
+  const bool row_ok = has_next && r_next < g.cin_rows;
+  const float* xk = g.cin_xk + r_next * g.cin_ldk;
+  const int in_ = q0_next / hp, jn = q0_next - in_ * hp;
+  if (has_next) io.a = (row_ok && in_ < g.cin_m) ? __ldg(g.cin_t0 + r_next * g.cin_ld0 + in_) : 0.f;
+#pragma unroll
+  for (int c = 0; c < 4; ++c) {
+    float v[8] = {a * io.x[2 * c].x, a * io.x[2 * c].y, a * io.x[2 * c].z, a * io.x[2 * c].w,
+                  a * io.x[2 * c + 1].x, a * io.x[2 * c + 1].y, a * io.x[2 * c + 1].z, a * io.x[2 * c + 1].w};
+    if (has_next) {
+      const int jj = jn + 8 * c;
+      io.x[2 * c] = (row_ok && jj < h) ? __ldg(reinterpret_cast<const float4*>(xk + jj)) : make_float4(0.f, 0.f, 0.f, 0.f);
+      io.x[2 * c + 1] = (row_ok && jj + 4 < h) ? __ldg(reinterpret_cast<const float4*>(xk + jj) + 1)
+                                               : make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+    if (h & 7) {
+#pragma unroll
+      for (int e = 0; e < 8; ++e)
+        if (j + 8 * c + e >= h) v[e] = 0.f;
+    }
+    store_chunk(v, hi_row, lo_row, ((c0 + c) ^ (rr & 7)) << 4);
+  }
+}
+
 // DIN local-activation-unit input (deepctr/layers/core.py:96-101), generated the same way: row r = (b, t),
 //   A[r, :] = [ q_b , k_bt , q_b - k_bt , q_b * k_bt ]   (4 segments of E columns; E % 8 == 0)
 // cin_t0 = queries [B, ld0], cin_xk = keys (sample stride cin_ldk, row stride E), cin_m = T, cin_h = E.
@@ -960,6 +1011,43 @@ __global__ void __launch_bounds__(WsLayout<CIN>::kThreads, 1)
       decode(tile, mt, nt, kbeg, nkb);
       const int64_t m0 = (mt * NCTA + cta_rank) * kTM;
       const int32_t n0 = (int32_t)(nt * BN + (int64_t)cta_rank * BNH);
+      if (g.cin_on == 1 && g.gen_groups == 1) {
+        // CIN, 256 threads per stage (two per generated row), software-pipelined: the loads of k-block kb + 1 are
+        // issued while k-block kb is multiplied, split and stored, and stay in flight across the stage hand-over
+        const int half = tid & 1;
+        const int atom = tid >> 7, rr = g.a_mn ? (tid & 127) >> 1 : tid >> 1;
+        const int64_t rfix = g.a_mn ? (int64_t)rr : m0 + rr;                 // + k0 when A is MN-major
+        const int qfix = g.a_mn ? (int)(m0 + atom * 64 + half * 32) : half * 32;   // + k0 when A is K-major
+        const int soff = (g.a_mn ? atom * 8192 : 0) + rr * 128;
+        CinRegs cur;
+        if (nkb > 0) cin_load_half(g, g.a_mn ? rfix + kbeg : rfix, g.a_mn ? qfix : qfix + (int)kbeg, cur);
+        for (int kb = 0; kb < nkb; ++kb, ++it) {
+          const int64_t k0 = kbeg + (int64_t)kb * kTK;
+          const int s = it % STAGES;
+          mbar_wait(&empty_bar[s], ((it / STAGES) & 1) ^ 1);
+          unsigned char* stp = tiles + (size_t)s * STAGE;
+          if (tid == 0) {
+            uint64_t* bar = &full_bar[s];
+            mbar_expect_tx(bar, (uint32_t)(2 * B_PLANE));
+            const uint32_t st = smem_u32(stp);
+            if (g.b_mn) {
+#pragma unroll
+              for (int j = 0; j < (BNH >= 64 ? BNH / 64 : 1); ++j) {
+                tma_load_2d(st + 2 * A_PLANE + j * 8192, &tm_bh, n0 + 64 * j, (int32_t)k0, bar);
+                tma_load_2d(st + 2 * A_PLANE + B_PLANE + j * 8192, &tm_bl, n0 + 64 * j, (int32_t)k0, bar);
+              }
+            } else {
+              tma_load_2d(st + 2 * A_PLANE, &tm_bh, (int32_t)k0, n0, bar);
+              tma_load_2d(st + 2 * A_PLANE + B_PLANE, &tm_bl, (int32_t)k0, n0, bar);
+            }
+          }
+          cin_emit_half(g, cur, g.a_mn ? qfix : qfix + (int)k0, stp + soff, stp + A_PLANE + soff, rr, half * 4,
+                        kb + 1 < nkb, g.a_mn ? rfix + k0 + kTK : rfix, g.a_mn ? qfix : qfix + (int)(k0 + kTK));
+          asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+          mbar_arrive(&full_bar[s]);
+        }
+        continue;
+      }
       for (int kb = 0; kb < nkb; ++kb, ++it) {
         const bool two = g.gen_groups == 2;
         if (two && (int)(it & 1) != grp) continue;

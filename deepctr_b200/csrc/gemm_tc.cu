@@ -821,11 +821,13 @@ __device__ __forceinline__ void cin_generate_half(const PlaneArgs& g, int64_t r,
 
 // The same half row in two steps, so that the producer loop can issue the global loads of k-block kb + 1 before it
 // multiplies / splits / stores k-block kb (the generator is load-latency-bound: its operands come from L2).
-struct CinRegs {
-  float a;
-  float4 x[8];
+struct GenRegs {       // one register image for both generators (only one of them runs in a launch)
+  float4 x[8];         // CIN: 32 values of X_k;  attention: 32 key values
+  float a;             // CIN: T0[r, i]
+  const float* q;      // attention: the row's query values
+  bool ok;             // attention: row inside the matrix
 };
-__device__ __forceinline__ void cin_load_half(const PlaneArgs& g, int64_t r, int q0, CinRegs& o) {
+__device__ __forceinline__ void cin_load_half(const PlaneArgs& g, int64_t r, int q0, GenRegs& o) {
   const bool row_ok = r < g.cin_rows;
   const float* xk = g.cin_xk + r * g.cin_ldk;
   const int hp = g.cin_hp, h = g.cin_h;
@@ -841,7 +843,7 @@ __device__ __forceinline__ void cin_load_half(const PlaneArgs& g, int64_t r, int
 }
 // multiply / split / store the half row held in `io` (k-block kb) and refill each register pair with the operands
 // of k-block kb + 1 as soon as it has been consumed: a rolling prefetch that costs no extra registers.
-__device__ __forceinline__ void cin_emit_half(const PlaneArgs& g, CinRegs& io, int q0, unsigned char* hi_row,
+__device__ __forceinline__ void cin_emit_half(const PlaneArgs& g, GenRegs& io, int q0, unsigned char* hi_row,
                                               unsigned char* lo_row, int rr, int c0, bool has_next, int64_t r_next,
                                               int q0_next) {
   const int hp = g.cin_hp, h = g.cin_h;
@@ -903,6 +905,61 @@ __device__ __forceinline__ void att_generate_half(const PlaneArgs& g, int64_t r,
     store_chunk(v, hi_row, lo_row, ((c0 + c) ^ (rr & 7)) << 4);
   }
 }
+// Attention input with the thread's 32 key values RESIDENT in registers (64 % E == 0, E >= 32: a thread's e-range
+// is the same in every k-block).  A forward tile (4E / 64 k-blocks over the same rows) then loads its keys once - and
+// the keys of the NEXT tile (or, kernel gradient, of the next k-block's rows) are loaded into the same registers as
+// soon as the last use of each pair has issued: the loads stay in flight across the stage hand-over.  The query
+// values come from L1 (a CTA's 128 rows belong to 3-4 samples).
+__device__ __forceinline__ void att_locate(const PlaneArgs& g, int64_t r, int e0, const float*& q, const float*& k,
+                                           bool& ok) {
+  const int T = g.cin_m, E = g.cin_h;
+  ok = r < g.cin_rows;
+  const uint32_t bu = ok ? (uint32_t)r / (uint32_t)T : 0u;
+  const int t = ok ? (int)((uint32_t)r - bu * (uint32_t)T) : 0;
+  q = g.cin_t0 + (int64_t)bu * g.cin_ld0 + e0;
+  k = g.cin_xk + (int64_t)bu * g.cin_ldk + (int64_t)t * E + e0;
+}
+__device__ __forceinline__ void att_load_keys(const PlaneArgs& g, int64_t r, int col0, GenRegs& o) {
+  const int E = g.cin_h;
+  const float* k;
+  att_locate(g, r, col0 - (col0 / E) * E, o.q, k, o.ok);
+#pragma unroll
+  for (int c = 0; c < 8; ++c)
+    o.x[c] = o.ok ? __ldg(reinterpret_cast<const float4*>(k) + c) : make_float4(0.f, 0.f, 0.f, 0.f);
+}
+__device__ __forceinline__ void att_emit_half(const PlaneArgs& g, GenRegs& io, int col0, unsigned char* hi_row,
+                                              unsigned char* lo_row, int rr, int c0, bool reload, int64_t r_next) {
+  const int E = g.cin_h;
+  const int seg = col0 / E;
+  const float* q = io.q;
+  const bool ok = io.ok;
+  const float* kn = nullptr;
+  bool okn = false;
+  if (reload) att_locate(g, r_next, col0 - seg * E, io.q, kn, okn);
+#pragma unroll
+  for (int c = 0; c < 4; ++c) {
+    const float4 k0 = io.x[2 * c], k1 = io.x[2 * c + 1];
+    float4 q0 = make_float4(0.f, 0.f, 0.f, 0.f), q1 = q0;
+    if (ok && seg != 1 && seg < 4) {
+      q0 = __ldg(reinterpret_cast<const float4*>(q) + 2 * c);
+      q1 = __ldg(reinterpret_cast<const float4*>(q) + 2 * c + 1);
+    }
+    if (reload) {
+      io.x[2 * c] = okn ? __ldg(reinterpret_cast<const float4*>(kn) + 2 * c) : make_float4(0.f, 0.f, 0.f, 0.f);
+      io.x[2 * c + 1] = okn ? __ldg(reinterpret_cast<const float4*>(kn) + 2 * c + 1) : make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+    const float qa[8] = {q0.x, q0.y, q0.z, q0.w, q1.x, q1.y, q1.z, q1.w};
+    const float ka[8] = {k0.x, k0.y, k0.z, k0.w, k1.x, k1.y, k1.z, k1.w};
+    float v[8];
+#pragma unroll
+    for (int jx = 0; jx < 8; ++jx)
+      v[jx] = seg == 0 ? qa[jx] : seg == 1 ? ka[jx] : seg == 2 ? __fsub_rn(qa[jx], ka[jx])
+            : seg == 3 ? __fmul_rn(qa[jx], ka[jx]) : 0.f;       // seg >= 4: columns of the M padding (kernel gradient)
+    store_chunk(v, hi_row, lo_row, ((c0 + c) ^ (rr & 7)) << 4);
+  }
+  if (reload) io.ok = okn;
+}
+
 __device__ __forceinline__ void generate_half(const PlaneArgs& g, int64_t r, int q0, unsigned char* hi_row,
                                               unsigned char* lo_row, int rr, int c0) {
   if (g.cin_on == 2) att_generate_half(g, r, q0, hi_row, lo_row, rr, c0);
@@ -1005,49 +1062,89 @@ __global__ void __launch_bounds__(WsLayout<CIN>::kThreads, 1)
     const int grp = tid >> 7, t128 = tid & 127;
     if (t128 == 0) { tma_prefetch_desc(&tm_bh); tma_prefetch_desc(&tm_bl); }
     uint32_t it = 0;
+    const bool att_res = g.cin_on == 2 && g.cin_h >= 32 && 64 % g.cin_h == 0;
+    if (g.gen_groups == 1 && (g.cin_on == 1 || att_res)) {
+      // 256 threads per stage (two per generated row), software-pipelined over the FLATTENED sequence of k-blocks
+      // of all the tiles of this CTA: the operands of the next k-block (the next tile's first one included) are
+      // requested while the current one is multiplied / split / stored, and stay in flight across the stage
+      // hand-over.  The generator was load-latency-bound (ncu source page: the stall samples sit on the first use
+      // of the loaded operands); with K = 4E = 256 the attention GEMM has only 4 k-blocks per tile.
+      const int half = tid & 1;
+      const int atom = tid >> 7, rr = g.a_mn ? (tid & 127) >> 1 : tid >> 1;
+      const int soff = (g.a_mn ? atom * 8192 : 0) + rr * 128;
+      // (32-bit coordinates: rows, columns and tile counts of the generated-operand GEMMs fit 31 bits, checked on
+      // the host; the state of two k-blocks stays in registers next to the prefetched operands)
+      const int ntiles = (int)w.ntiles, stride = (int)nclusters;
+      auto dec = [&](int tile, int& m0, int& n0, int& kbeg, int& nkb) {
+        int64_t mt, nt, kb64;
+        decode(tile, mt, nt, kb64, nkb);
+        m0 = (int)((mt * NCTA + cta_rank) * kTM);
+        n0 = (int)(nt * BN + (int64_t)cta_rank * BNH);
+        kbeg = (int)kb64;
+      };
+      int tile = (int)cluster_id, m0 = 0, n0 = 0, kbeg = 0, nkb = 0, kb = 0;
+      for (; tile < ntiles; tile += stride) {            // first tile with work
+        dec(tile, m0, n0, kbeg, nkb);
+        if (nkb > 0) break;
+      }
+      // this thread's row and first column in the k-block at (m0, k0)
+      auto row_of = [&](int m0_, int k0_) { return g.a_mn ? k0_ + rr : m0_ + rr; };
+      auto col_of = [&](int m0_, int k0_) { return g.a_mn ? m0_ + atom * 64 + half * 32 : k0_ + half * 32; };
+      GenRegs gr;
+      if (tile < ntiles) {
+        if (g.cin_on == 1) cin_load_half(g, row_of(m0, kbeg), col_of(m0, kbeg), gr);
+        else att_load_keys(g, row_of(m0, kbeg), col_of(m0, kbeg), gr);
+      }
+      while (tile < ntiles) {
+        const int k0 = kbeg + kb * kTK;
+        // the k-block after this one
+        int tile_n = tile, m0_n = m0, n0_n = n0, kbeg_n = kbeg, nkb_n = nkb, kb_n = kb + 1;
+        if (kb_n >= nkb) {
+          kb_n = 0;
+          for (tile_n = tile + stride; tile_n < ntiles; tile_n += stride) {
+            dec(tile_n, m0_n, n0_n, kbeg_n, nkb_n);
+            if (nkb_n > 0) break;
+          }
+        }
+        const bool has_next = tile_n < ntiles;
+        const int k0_n = kbeg_n + kb_n * kTK;
+        const int s = it % STAGES;
+        mbar_wait(&empty_bar[s], ((it / STAGES) & 1) ^ 1);
+        unsigned char* stp = tiles + (size_t)s * STAGE;
+        if (tid == 0) {
+          uint64_t* bar = &full_bar[s];
+          mbar_expect_tx(bar, (uint32_t)(2 * B_PLANE));
+          const uint32_t st = smem_u32(stp);
+          if (g.b_mn) {
+#pragma unroll
+            for (int j = 0; j < (BNH >= 64 ? BNH / 64 : 1); ++j) {
+              tma_load_2d(st + 2 * A_PLANE + j * 8192, &tm_bh, n0 + 64 * j, k0, bar);
+              tma_load_2d(st + 2 * A_PLANE + B_PLANE + j * 8192, &tm_bl, n0 + 64 * j, k0, bar);
+            }
+          } else {
+            tma_load_2d(st + 2 * A_PLANE, &tm_bh, k0, n0, bar);
+            tma_load_2d(st + 2 * A_PLANE + B_PLANE, &tm_bl, k0, n0, bar);
+          }
+        }
+        if (g.cin_on == 1) {
+          cin_emit_half(g, gr, col_of(m0, k0), stp + soff, stp + A_PLANE + soff, rr, half * 4, has_next,
+                        row_of(m0_n, k0_n), col_of(m0_n, k0_n));
+        } else {
+          const int r = row_of(m0, k0), r_n = row_of(m0_n, k0_n);
+          att_emit_half(g, gr, col_of(m0, k0), stp + soff, stp + A_PLANE + soff, rr, half * 4, has_next && r_n != r, r_n);
+        }
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+        mbar_arrive(&full_bar[s]);
+        ++it;
+        tile = tile_n; m0 = m0_n; n0 = n0_n; kbeg = kbeg_n; nkb = nkb_n; kb = kb_n;
+      }
+    } else
     for (int64_t tile = cluster_id; tile < w.ntiles; tile += nclusters) {
       int64_t mt, nt, kbeg;
       int nkb;
       decode(tile, mt, nt, kbeg, nkb);
       const int64_t m0 = (mt * NCTA + cta_rank) * kTM;
       const int32_t n0 = (int32_t)(nt * BN + (int64_t)cta_rank * BNH);
-      if (g.cin_on == 1 && g.gen_groups == 1) {
-        // CIN, 256 threads per stage (two per generated row), software-pipelined: the loads of k-block kb + 1 are
-        // issued while k-block kb is multiplied, split and stored, and stay in flight across the stage hand-over
-        const int half = tid & 1;
-        const int atom = tid >> 7, rr = g.a_mn ? (tid & 127) >> 1 : tid >> 1;
-        const int64_t rfix = g.a_mn ? (int64_t)rr : m0 + rr;                 // + k0 when A is MN-major
-        const int qfix = g.a_mn ? (int)(m0 + atom * 64 + half * 32) : half * 32;   // + k0 when A is K-major
-        const int soff = (g.a_mn ? atom * 8192 : 0) + rr * 128;
-        CinRegs cur;
-        if (nkb > 0) cin_load_half(g, g.a_mn ? rfix + kbeg : rfix, g.a_mn ? qfix : qfix + (int)kbeg, cur);
-        for (int kb = 0; kb < nkb; ++kb, ++it) {
-          const int64_t k0 = kbeg + (int64_t)kb * kTK;
-          const int s = it % STAGES;
-          mbar_wait(&empty_bar[s], ((it / STAGES) & 1) ^ 1);
-          unsigned char* stp = tiles + (size_t)s * STAGE;
-          if (tid == 0) {
-            uint64_t* bar = &full_bar[s];
-            mbar_expect_tx(bar, (uint32_t)(2 * B_PLANE));
-            const uint32_t st = smem_u32(stp);
-            if (g.b_mn) {
-#pragma unroll
-              for (int j = 0; j < (BNH >= 64 ? BNH / 64 : 1); ++j) {
-                tma_load_2d(st + 2 * A_PLANE + j * 8192, &tm_bh, n0 + 64 * j, (int32_t)k0, bar);
-                tma_load_2d(st + 2 * A_PLANE + B_PLANE + j * 8192, &tm_bl, n0 + 64 * j, (int32_t)k0, bar);
-              }
-            } else {
-              tma_load_2d(st + 2 * A_PLANE, &tm_bh, (int32_t)k0, n0, bar);
-              tma_load_2d(st + 2 * A_PLANE + B_PLANE, &tm_bl, (int32_t)k0, n0, bar);
-            }
-          }
-          cin_emit_half(g, cur, g.a_mn ? qfix : qfix + (int)k0, stp + soff, stp + A_PLANE + soff, rr, half * 4,
-                        kb + 1 < nkb, g.a_mn ? rfix + k0 + kTK : rfix, g.a_mn ? qfix : qfix + (int)(k0 + kTK));
-          asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-          mbar_arrive(&full_bar[s]);
-        }
-        continue;
-      }
       for (int kb = 0; kb < nkb; ++kb, ++it) {
         const bool two = g.gen_groups == 2;
         if (two && (int)(it & 1) != grp) continue;
@@ -1768,8 +1865,9 @@ static b2ctr_status_t gen_gemm(const GenSpec& sp, int mode, int64_t n, const voi
     static int groups = -1;
     if (groups < 0) { const char* ev = getenv("B2CTR_GEN_GROUPS"); groups = ev ? atoi(ev) : 0; }
     // measured (profiles/README.md): the CIN generator is faster with all 256 threads on every stage (C3 8.02 vs
-    // 8.32 ms), the attention generator with two groups alternating stages (C4 3.55 vs 3.59 ms)
-    pa.gen_groups = groups == 1 || groups == 2 ? groups : (sp.kind == 1 ? 1 : 2);
+    // 8.32 ms), the (non-resident) attention generator with two groups alternating stages (C4 3.55 vs 3.59 ms)
+    // (the attention generator keeps its keys in registers when a thread's e-range is fixed: 64 % E == 0, E >= 32)
+    pa.gen_groups = groups == 1 || groups == 2 ? groups : (sp.kind == 1 || (sp.h >= 32 && 64 % sp.h == 0) ? 1 : 2);
   }
   pa.b_mn = 1;      // both B operands are row-major matrices whose reduction dim is their row index
   pa.c = c; pa.bias = bias; pa.ws = (float*)workspace; pa.ldc = ldc;

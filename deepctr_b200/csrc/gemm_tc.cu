@@ -845,7 +845,7 @@ __device__ __forceinline__ void cin_load_half(const PlaneArgs& g, int64_t r, int
 // of k-block kb + 1 as soon as it has been consumed: a rolling prefetch that costs no extra registers.
 __device__ __forceinline__ void cin_emit_half(const PlaneArgs& g, GenRegs& io, int q0, unsigned char* hi_row,
                                               unsigned char* lo_row, int rr, int c0, bool has_next, int64_t r_next,
-                                              int q0_next) {
+                                              int q0_next, bool reload_x) {
   const int hp = g.cin_hp, h = g.cin_h;
   const int j = q0 - (q0 / hp) * hp;
   const float a = io.a;
@@ -857,7 +857,7 @@ __device__ __forceinline__ void cin_emit_half(const PlaneArgs& g, GenRegs& io, i
   for (int c = 0; c < 4; ++c) {
     float v[8] = {a * io.x[2 * c].x, a * io.x[2 * c].y, a * io.x[2 * c].z, a * io.x[2 * c].w,
                   a * io.x[2 * c + 1].x, a * io.x[2 * c + 1].y, a * io.x[2 * c + 1].z, a * io.x[2 * c + 1].w};
-    if (has_next) {
+    if (reload_x) {       // (the next k-block may need the same 32 values of X_k: they then stay where they are)
       const int jj = jn + 8 * c;
       io.x[2 * c] = (row_ok && jj < h) ? __ldg(reinterpret_cast<const float4*>(xk + jj)) : make_float4(0.f, 0.f, 0.f, 0.f);
       io.x[2 * c + 1] = (row_ok && jj + 4 < h) ? __ldg(reinterpret_cast<const float4*>(xk + jj) + 1)
@@ -1092,11 +1092,22 @@ __global__ void __launch_bounds__(WsLayout<CIN>::kThreads, 1)
       auto col_of = [&](int m0_, int k0_) { return g.a_mn ? m0_ + atom * 64 + half * 32 : k0_ + half * 32; };
       GenRegs gr;
       if (tile < ntiles) {
-        if (g.cin_on == 1) cin_load_half(g, row_of(m0, kbeg), col_of(m0, kbeg), gr);
+        if (g.cin_on == 1) cin_load_half(g, row_of(m0, kbeg), col_of(m0, kbeg), gr);     // (k_of(kbeg, 0, .) == kbeg)
         else att_load_keys(g, row_of(m0, kbeg), col_of(m0, kbeg), gr);
       }
+      // CIN forward, hp = nj * 64: the k-blocks of a tile are walked j-block-major (all i for the first 64 columns of
+      // X_k, then all i for the next 64 ...).  A thread's 32 values of X_k are then the same for m consecutive
+      // k-blocks and stay in registers; only T0[r, i] is fetched per k-block.  (The B planes are fetched at the same
+      // k0, and the order of the K accumulation is free.)
+      const int nj = (g.cin_on == 1 && !g.a_mn && g.splits == 1 && g.cin_hp >= 128) ? g.cin_hp / kTK : 1;
+      auto k_of = [&](int kbeg_, int kb_, int nkb_) {
+        if (nj == 1) return kbeg_ + kb_ * kTK;
+        const int ni = nkb_ / nj;                      // = m (k_pad = m * hp)
+        const int jb = kb_ / ni, i = kb_ - jb * ni;
+        return (i * nj + jb) * kTK;
+      };
       while (tile < ntiles) {
-        const int k0 = kbeg + kb * kTK;
+        const int k0 = k_of(kbeg, kb, nkb);
         // the k-block after this one
         int tile_n = tile, m0_n = m0, n0_n = n0, kbeg_n = kbeg, nkb_n = nkb, kb_n = kb + 1;
         if (kb_n >= nkb) {
@@ -1107,7 +1118,7 @@ __global__ void __launch_bounds__(WsLayout<CIN>::kThreads, 1)
           }
         }
         const bool has_next = tile_n < ntiles;
-        const int k0_n = kbeg_n + kb_n * kTK;
+        const int k0_n = k_of(kbeg_n, kb_n, nkb_n);
         const int s = it % STAGES;
         mbar_wait(&empty_bar[s], ((it / STAGES) & 1) ^ 1);
         unsigned char* stp = tiles + (size_t)s * STAGE;
@@ -1127,8 +1138,9 @@ __global__ void __launch_bounds__(WsLayout<CIN>::kThreads, 1)
           }
         }
         if (g.cin_on == 1) {
-          cin_emit_half(g, gr, col_of(m0, k0), stp + soff, stp + A_PLANE + soff, rr, half * 4, has_next,
-                        row_of(m0_n, k0_n), col_of(m0_n, k0_n));
+          const int r = row_of(m0, k0), r_n = row_of(m0_n, k0_n), q = col_of(m0, k0), q_n = col_of(m0_n, k0_n);
+          cin_emit_half(g, gr, q, stp + soff, stp + A_PLANE + soff, rr, half * 4, has_next, r_n, q_n,
+                        has_next && (r_n != r || q_n % g.cin_hp != q % g.cin_hp));
         } else {
           const int r = row_of(m0, k0), r_n = row_of(m0_n, k0_n);
           att_emit_half(g, gr, col_of(m0, k0), stp + soff, stp + A_PLANE + soff, rr, half * 4, has_next && r_n != r, r_n);

@@ -42,6 +42,31 @@ def main():
         out["fit_%d_steps_ms" % steps] = (time.perf_counter() - t0) * 1e3
     out["per_step_ms"] = (out["fit_80_steps_ms"] - out["fit_20_steps_ms"]) / 60.0
     out["fixed_ms"] = out["fit_20_steps_ms"] - 20 * out["per_step_ms"]
+    # timeline of one 20-step fit: host time of every step launch, device time at which every step finished
+    x, y = arrays(20)
+    orig = model._loss_step
+    host_t, evs = [], []
+
+    def traced(*a, **k):
+        host_t.append(time.perf_counter())
+        out_ = orig(*a, **k)
+        ev = torch.cuda.Event(enable_timing=True)
+        ev.record()
+        evs.append(ev)
+        return out_
+
+    model._loss_step = traced
+    torch.cuda.synchronize()
+    e0 = torch.cuda.Event(enable_timing=True)
+    e0.record()
+    t0 = time.perf_counter()
+    model.fit(x, y, batch_size=B, epochs=1, shuffle=False, verbose=0)
+    t1 = time.perf_counter()
+    torch.cuda.synchronize()
+    model._loss_step = orig
+    out["trace_fit_ms"] = (t1 - t0) * 1e3
+    out["trace_host_launch_ms"] = [round((t - t0) * 1e3, 3) for t in host_t]
+    out["trace_dev_done_ms"] = [round(e0.elapsed_time(e), 3) for e in evs]
     # producer stages in isolation (no training step running)
     x, y = arrays(40)
     from deepctr_b200.inputs import slice_inputs

@@ -781,46 +781,10 @@ __device__ __forceinline__ void store_chunk(const float (&v)[8], unsigned char* 
 }
 
 // Generated A operand, CIN: one producer thread = half a row r of the outer product per stage: 32 consecutive
-// q = i*hp + j starting at q0 (a multiple of 32; hp is 32 or a multiple of 64, so 8-element chunks never straddle
-// an i), split into bf16 hi/lo and stored as four 16-byte chunks [c0, c0+4) of the 128-byte-swizzled row `rr`.
-__device__ __forceinline__ void cin_generate_half(const PlaneArgs& g, int64_t r, int q0, unsigned char* hi_row,
-                                                  unsigned char* lo_row, int rr, int c0) {
-  const bool row_ok = r < g.cin_rows;
-  const float* xk = g.cin_xk + r * g.cin_ldk;
-  const float* t0 = g.cin_t0 + r * g.cin_ld0;
-  const int hp = g.cin_hp, h = g.cin_h;
-  int i = q0 / hp, j = q0 - i * hp;
-  float a = (row_ok && i < g.cin_m) ? __ldg(t0 + i) : 0.f;
-  float4 x[8];
-#pragma unroll
-  for (int c = 0; c < 4; ++c) {          // all eight 16-byte loads first (independent of a)
-    const int jj = j + 8 * c >= hp ? j + 8 * c - hp : j + 8 * c;
-    // h % 4 == 0 or the rows are padded to hp: a quad starting below h is inside the row
-    x[2 * c] = (row_ok && jj < h) ? __ldg(reinterpret_cast<const float4*>(xk + jj)) : make_float4(0.f, 0.f, 0.f, 0.f);
-    x[2 * c + 1] = (row_ok && jj + 4 < h) ? __ldg(reinterpret_cast<const float4*>(xk + jj) + 1)
-                                          : make_float4(0.f, 0.f, 0.f, 0.f);
-  }
-#pragma unroll
-  for (int c = 0; c < 4; ++c) {
-    float v[8] = {a * x[2 * c].x, a * x[2 * c].y, a * x[2 * c].z, a * x[2 * c].w,
-                  a * x[2 * c + 1].x, a * x[2 * c + 1].y, a * x[2 * c + 1].z, a * x[2 * c + 1].w};
-    if (h & 7) {                         // ragged h: zero the tail of the last chunk
-#pragma unroll
-      for (int e = 0; e < 8; ++e)
-        if (j + e >= h) v[e] = 0.f;
-    }
-    store_chunk(v, hi_row, lo_row, ((c0 + c) ^ (rr & 7)) << 4);
-    j += 8;
-    if (j >= hp) {                       // next i (only when hp == 32: two i per 64-deep k-block)
-      j = 0;
-      ++i;
-      a = (row_ok && i < g.cin_m) ? __ldg(t0 + i) : 0.f;
-    }
-  }
-}
-
-// The same half row in two steps, so that the producer loop can issue the global loads of k-block kb + 1 before it
-// multiplies / splits / stores k-block kb (the generator is load-latency-bound: its operands come from L2).
+// q = i*hp + j starting at q0 (a multiple of 32; hp is 32 or a multiple of 64, so the 32 columns share one i), split
+// into bf16 hi/lo and stored as four 16-byte chunks [c0, c0+4) of the 128-byte-swizzled row `rr`.
+// Two steps, so that the producer loop can issue the global loads of k-block kb + 1 before it multiplies / splits /
+// stores k-block kb.
 struct GenRegs {       // one register image for both generators (only one of them runs in a launch)
   float4 x[8];         // CIN: 32 values of X_k;  attention: 32 key values
   float a;             // CIN: T0[r, i]
@@ -875,7 +839,8 @@ __device__ __forceinline__ void cin_emit_half(const PlaneArgs& g, GenRegs& io, i
 // DIN local-activation-unit input (deepctr/layers/core.py:96-101), generated the same way: row r = (b, t),
 //   A[r, :] = [ q_b , k_bt , q_b - k_bt , q_b * k_bt ]   (4 segments of E columns; E % 8 == 0)
 // cin_t0 = queries [B, ld0], cin_xk = keys (sample stride cin_ldk, row stride E), cin_m = T, cin_h = E.
-__device__ __forceinline__ void att_generate_half(const PlaneArgs& g, int64_t r, int col0, unsigned char* hi_row,
+// (generic E: not inlined - one copy instead of eight in the producer loop)
+__device__ __noinline__ void att_generate_half(const PlaneArgs& g, int64_t r, int col0, unsigned char* hi_row,
                                                   unsigned char* lo_row, int rr, int c0) {
   const int T = g.cin_m, E = g.cin_h;
   const bool row_ok = r < g.cin_rows;
@@ -960,22 +925,19 @@ __device__ __forceinline__ void att_emit_half(const PlaneArgs& g, GenRegs& io, i
   if (reload) io.ok = okn;
 }
 
-__device__ __forceinline__ void generate_half(const PlaneArgs& g, int64_t r, int q0, unsigned char* hi_row,
-                                              unsigned char* lo_row, int rr, int c0) {
-  if (g.cin_on == 2) att_generate_half(g, r, q0, hi_row, lo_row, rr, c0);
-  else cin_generate_half(g, r, q0, hi_row, lo_row, rr, c0);
-}
 
 // generated-operand kernels run 8 producer warps (two threads per generated row), the others 4
-template <bool CIN>
+template <bool GENERATED>
 struct WsLayout {
-  static constexpr int kProducers = CIN ? 8 : kWsProducers;
+  static constexpr int kProducers = GENERATED ? 8 : kWsProducers;
   static constexpr int kMmaWarp = kWsEpilogueWarps + kProducers;
   static constexpr int kThreads = (kMmaWarp + 1) * 32;
 };
 
-template <int BN, int STAGES, int NCTA, bool TMA, bool CIN = false, bool FOLD = false>
-__global__ void __launch_bounds__(WsLayout<CIN>::kThreads, 1)
+// GEN: 0 = both operands from memory; 1 = A generated as the CIN outer product; 2 = A generated as the DIN
+// attention input (one instantiation per generator: the code of the other one would only fill the instruction cache)
+template <int BN, int STAGES, int NCTA, bool TMA, int GEN = 0, bool FOLD = false>
+__global__ void __launch_bounds__(WsLayout<GEN != 0>::kThreads, 1)
     gemm_planes_ws_kernel(const __grid_constant__ WsArgs w, const __grid_constant__ CUtensorMap tm_ah,
                           const __grid_constant__ CUtensorMap tm_al, const __grid_constant__ CUtensorMap tm_bh,
                           const __grid_constant__ CUtensorMap tm_bl) {
@@ -990,6 +952,7 @@ __global__ void __launch_bounds__(WsLayout<CIN>::kThreads, 1)
                                                           ~(uintptr_t)1023);
   __shared__ __align__(8) uint64_t full_bar[STAGES], peer_full[STAGES], empty_bar[STAGES], acc_full[2], acc_empty[2];
   __shared__ uint32_t tmem_slot;
+  unsigned char* epi_stage = tiles + (size_t)STAGES * STAGE;      // 8 epilogue warps x 4 KB (not in FOLD kernels)
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const uint32_t cta_rank = NCTA == 1 ? 0u : cluster_ctarank();
@@ -1000,7 +963,7 @@ __global__ void __launch_bounds__(WsLayout<CIN>::kThreads, 1)
       // cp.async producers: one deferred arrival per producer thread of THIS CTA; TMA: one arrive.expect_tx
       // CIN: the B planes arrive by TMA (1 arrive.expect_tx) + one arrival per generating thread
       // generated A: one group of 128 threads per stage + the TMA expect_tx of the B planes
-      mbar_init(&full_bar[s], CIN ? 1 + (g.gen_groups == 2 ? 128 : 256) : (TMA ? 1 : kWsProducers * 32));
+      mbar_init(&full_bar[s], GEN != 0 ? 1 + (g.gen_groups == 2 ? 128 : 256) : (TMA ? 1 : kWsProducers * 32));
       mbar_init(&peer_full[s], 1);                    // leader only: the peer CTA's half of the stage landed
       mbar_init(&empty_bar[s], 1);
     }
@@ -1010,7 +973,7 @@ __global__ void __launch_bounds__(WsLayout<CIN>::kThreads, 1)
     }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
-  if (warp == WsLayout<CIN>::kMmaWarp) {
+  if (warp == WsLayout<GEN != 0>::kMmaWarp) {
     if constexpr (NCTA == 1) {
       asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_slot)),
                    "r"(TMEM_COLS)
@@ -1050,8 +1013,8 @@ __global__ void __launch_bounds__(WsLayout<CIN>::kThreads, 1)
     nkb = kend > kbeg ? (int)((kend - kbeg) / kTK) : 0;
   };
 
-  constexpr int kMmaWarp = WsLayout<CIN>::kMmaWarp;
-  if (CIN && warp >= kWsEpilogueWarps && warp < kMmaWarp) {
+  constexpr int kMmaWarp = WsLayout<GEN != 0>::kMmaWarp;
+  if (GEN != 0 && warp >= kWsEpilogueWarps && warp < kMmaWarp) {
     // ------------------------------------------------------------------------------ generating producers
     // 8 warps in TWO GROUPS of 128 threads; group g owns the stages with (stage counter & 1) == g and generates a
     // whole row (64 columns) per thread for them.  Two stages are therefore in production at any time: while one
@@ -1062,8 +1025,8 @@ __global__ void __launch_bounds__(WsLayout<CIN>::kThreads, 1)
     const int grp = tid >> 7, t128 = tid & 127;
     if (t128 == 0) { tma_prefetch_desc(&tm_bh); tma_prefetch_desc(&tm_bl); }
     uint32_t it = 0;
-    const bool att_res = g.cin_on == 2 && g.cin_h >= 32 && 64 % g.cin_h == 0;
-    if (g.gen_groups == 1 && (g.cin_on == 1 || att_res)) {
+    const bool att_res = GEN == 2 && g.cin_h >= 32 && 64 % g.cin_h == 0;
+    if (GEN == 1 || (att_res && g.gen_groups == 1)) {
       // 256 threads per stage (two per generated row), software-pipelined over the FLATTENED sequence of k-blocks
       // of all the tiles of this CTA: the operands of the next k-block (the next tile's first one included) are
       // requested while the current one is multiplied / split / stored, and stay in flight across the stage
@@ -1092,14 +1055,14 @@ __global__ void __launch_bounds__(WsLayout<CIN>::kThreads, 1)
       auto col_of = [&](int m0_, int k0_) { return g.a_mn ? m0_ + atom * 64 + half * 32 : k0_ + half * 32; };
       GenRegs gr;
       if (tile < ntiles) {
-        if (g.cin_on == 1) cin_load_half(g, row_of(m0, kbeg), col_of(m0, kbeg), gr);     // (k_of(kbeg, 0, .) == kbeg)
+        if constexpr (GEN == 1) cin_load_half(g, row_of(m0, kbeg), col_of(m0, kbeg), gr);     // (k_of(kbeg, 0, .) == kbeg)
         else att_load_keys(g, row_of(m0, kbeg), col_of(m0, kbeg), gr);
       }
       // CIN forward, hp = nj * 64: the k-blocks of a tile are walked j-block-major (all i for the first 64 columns of
       // X_k, then all i for the next 64 ...).  A thread's 32 values of X_k are then the same for m consecutive
       // k-blocks and stay in registers; only T0[r, i] is fetched per k-block.  (The B planes are fetched at the same
       // k0, and the order of the K accumulation is free.)
-      const int nj = (g.cin_on == 1 && !g.a_mn && g.splits == 1 && g.cin_hp >= 128) ? g.cin_hp / kTK : 1;
+      const int nj = (GEN == 1 && !g.a_mn && g.splits == 1 && g.cin_hp >= 128) ? g.cin_hp / kTK : 1;
       auto k_of = [&](int kbeg_, int kb_, int nkb_) {
         if (nj == 1) return kbeg_ + kb_ * kTK;
         const int ni = nkb_ / nj;                      // = m (k_pad = m * hp)
@@ -1137,7 +1100,7 @@ __global__ void __launch_bounds__(WsLayout<CIN>::kThreads, 1)
             tma_load_2d(st + 2 * A_PLANE + B_PLANE, &tm_bl, k0, n0, bar);
           }
         }
-        if (g.cin_on == 1) {
+        if constexpr (GEN == 1) {
           const int r = row_of(m0, k0), r_n = row_of(m0_n, k0_n), q = col_of(m0, k0), q_n = col_of(m0_n, k0_n);
           cin_emit_half(g, gr, q, stp + soff, stp + A_PLANE + soff, rr, half * 4, has_next, r_n, q_n,
                         has_next && (r_n != r || q_n % g.cin_hp != q % g.cin_hp));
@@ -1183,22 +1146,22 @@ __global__ void __launch_bounds__(WsLayout<CIN>::kThreads, 1)
           if (g.a_mn) {      // A^T: M = q (two 64-wide atoms), K = r: thread -> (atom, k-row)
             const int atom = t128 >> 6, rr = t128 & 63;
             unsigned char* row = stp + atom * 8192 + rr * 128;
-            generate_half(g, k0 + rr, (int)(m0 + atom * 64), row, row + A_PLANE, rr, 0);
-            generate_half(g, k0 + rr, (int)(m0 + atom * 64 + 32), row, row + A_PLANE, rr, 4);
+            att_generate_half(g, k0 + rr, (int)(m0 + atom * 64), row, row + A_PLANE, rr, 0);
+            att_generate_half(g, k0 + rr, (int)(m0 + atom * 64 + 32), row, row + A_PLANE, rr, 4);
           } else {           // A: M = r, K = q: thread -> row
             unsigned char* row = stp + t128 * 128;
-            generate_half(g, m0 + t128, (int)k0, row, row + A_PLANE, t128, 0);
-            generate_half(g, m0 + t128, (int)(k0 + 32), row, row + A_PLANE, t128, 4);
+            att_generate_half(g, m0 + t128, (int)k0, row, row + A_PLANE, t128, 0);
+            att_generate_half(g, m0 + t128, (int)(k0 + 32), row, row + A_PLANE, t128, 4);
           }
         } else {
           const int half = tid & 1;           // two threads per generated row: 32 of its 64 columns each
           if (g.a_mn) {
             const int atom = tid >> 7, rr = (tid & 127) >> 1;
-            generate_half(g, k0 + rr, (int)(m0 + atom * 64 + half * 32), stp + atom * 8192 + rr * 128,
+            att_generate_half(g, k0 + rr, (int)(m0 + atom * 64 + half * 32), stp + atom * 8192 + rr * 128,
                           stp + A_PLANE + atom * 8192 + rr * 128, rr, half * 4);
           } else {
             const int rr = tid >> 1;
-            generate_half(g, m0 + rr, (int)(k0 + half * 32), stp + rr * 128, stp + A_PLANE + rr * 128, rr, half * 4);
+            att_generate_half(g, m0 + rr, (int)(k0 + half * 32), stp + rr * 128, stp + A_PLANE + rr * 128, rr, half * 4);
           }
         }
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
@@ -1473,7 +1436,12 @@ __global__ void __launch_bounds__(WsLayout<CIN>::kThreads, 1)
         mbar_wait(&acc_full[ab], (acc_it >> 1) & 1);
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
       }
-      const int64_t gm = (mt * NCTA + cta_rank) * kTM + sub * 32 + lane;
+      // The accumulator arrives lane = row (tcgen05.ld 32x32b): a direct store would put the 32 lanes of every
+      // instruction in 32 different rows of C (16 bytes each, half a sector per lane - measured: ~4 us per
+      // 256 x 128 tile, the whole cost of a short-K tile).  Each warp therefore turns its 32 x 32 block through a
+      // 4 KB XOR-swizzled staging buffer and stores 8 lanes = 128 contiguous bytes per row, 4 rows per instruction.
+      const int64_t row_base = (mt * NCTA + cta_rank) * kTM + sub * 32;
+      unsigned char* stg = epi_stage + warp * 4096;
       if (half < HALVES) {
 #pragma unroll 1
         for (int c0 = half * COLS; c0 < (half + 1) * COLS; c0 += 32) {
@@ -1497,55 +1465,74 @@ __global__ void __launch_bounds__(WsLayout<CIN>::kThreads, 1)
 #pragma unroll
             for (int j = 0; j < 32; ++j) r[j] = 0u;
           }
-          if (gm >= g.m) continue;
-          if (g.splits > 1) {
-            float* wrow = g.ws + (z * g.m + gm) * g.n + gn0;
-            if (vec_ws && gn0 + 32 <= g.n) {
+          if (row_base >= g.m) continue;   // warp-uniform: the whole 32-row block is padding
 #pragma unroll
-              for (int j = 0; j < 32; j += 4)
-                *reinterpret_cast<float4*>(wrow + j) =
-                    make_float4(g.alpha * __uint_as_float(r[j]), g.alpha * __uint_as_float(r[j + 1]),
-                                g.alpha * __uint_as_float(r[j + 2]), g.alpha * __uint_as_float(r[j + 3]));
-            } else {
-#pragma unroll
-              for (int j = 0; j < 32; ++j)
-                if (gn0 + j < g.n) wrow[j] = g.alpha * __uint_as_float(r[j]);
-            }
-          } else if (vec_c && gn0 + 32 <= g.n) {
-            float* crow = g.c + gm * g.ldc + gn0;
-            const bool relu = g.act == B2CTR_ACT_RELU, other = g.act != B2CTR_ACT_NONE && !relu;
-#pragma unroll
-            for (int j = 0; j < 32; j += 4) {
-              float4 v = make_float4(g.alpha * __uint_as_float(r[j]), g.alpha * __uint_as_float(r[j + 1]),
-                                     g.alpha * __uint_as_float(r[j + 2]), g.alpha * __uint_as_float(r[j + 3]));
-              if (g.accumulate) {
-                const float4 o = *reinterpret_cast<const float4*>(crow + j);
-                v.x += o.x; v.y += o.y; v.z += o.z; v.w += o.w;
-              }
-              if (g.bias) {
-                const float4 bb = __ldg(reinterpret_cast<const float4*>(g.bias + gn0 + j));
-                v.x += bb.x; v.y += bb.y; v.z += bb.z; v.w += bb.w;
-              }
-              if (relu) {
-                v.x = fmaxf(v.x, 0.f); v.y = fmaxf(v.y, 0.f); v.z = fmaxf(v.z, 0.f); v.w = fmaxf(v.w, 0.f);
-              } else if (other) {
-                v.x = act_apply(v.x, g.act); v.y = act_apply(v.y, g.act);
-                v.z = act_apply(v.z, g.act); v.w = act_apply(v.w, g.act);
-              }
-              *reinterpret_cast<float4*>(crow + j) = v;
-            }
-          } else {
-#pragma unroll
-            for (int j = 0; j < 32; ++j) {
-              const int64_t gn = gn0 + j;
-              if (gn < g.n) {
-                float v = g.alpha * __uint_as_float(r[j]);
-                if (g.accumulate) v += g.c[gm * g.ldc + gn];
-                if (g.bias) v += g.bias[gn];
-                g.c[gm * g.ldc + gn] = act_apply(v, g.act);
-              }
+          for (int c = 0; c < 8; ++c)      // row `lane`, 16-byte chunk c -> physical chunk c ^ (lane & 7)
+            *reinterpret_cast<uint4*>(stg + lane * 128 + ((c ^ (lane & 7)) << 4)) =
+                make_uint4(r[4 * c], r[4 * c + 1], r[4 * c + 2], r[4 * c + 3]);
+          __syncwarp();
+          const int chunk = lane & 7;
+          const int64_t gn = gn0 + chunk * 4;
+          const bool full4 = gn + 4 <= g.n;
+          float4 bb = make_float4(0.f, 0.f, 0.f, 0.f);
+          if (g.bias && g.splits == 1 && gn < g.n) {
+            if (full4 && vec_c) bb = __ldg(reinterpret_cast<const float4*>(g.bias + gn));
+            else {
+              bb.x = g.bias[gn];
+              if (gn + 1 < g.n) bb.y = g.bias[gn + 1];
+              if (gn + 2 < g.n) bb.z = g.bias[gn + 2];
+              if (gn + 3 < g.n) bb.w = g.bias[gn + 3];
             }
           }
+          const bool relu = g.act == B2CTR_ACT_RELU, other = g.act != B2CTR_ACT_NONE && !relu;
+#pragma unroll 2
+          for (int i = 0; i < 8; ++i) {
+            const int row = i * 4 + (lane >> 3);
+            const uint4 u = *reinterpret_cast<const uint4*>(stg + row * 128 + ((chunk ^ (row & 7)) << 4));
+            const int64_t gm = row_base + row;
+            if (gm >= g.m || gn >= g.n) continue;
+            float4 v = make_float4(g.alpha * __uint_as_float(u.x), g.alpha * __uint_as_float(u.y),
+                                   g.alpha * __uint_as_float(u.z), g.alpha * __uint_as_float(u.w));
+            if (g.splits > 1) {
+              float* wrow = g.ws + (z * g.m + gm) * g.n + gn;
+              if (vec_ws && full4) *reinterpret_cast<float4*>(wrow) = v;
+              else {
+                wrow[0] = v.x;
+                if (gn + 1 < g.n) wrow[1] = v.y;
+                if (gn + 2 < g.n) wrow[2] = v.z;
+                if (gn + 3 < g.n) wrow[3] = v.w;
+              }
+              continue;
+            }
+            float* crow = g.c + gm * g.ldc + gn;
+            const bool vec = vec_c && full4;
+            if (g.accumulate) {
+              if (vec) {
+                const float4 o = *reinterpret_cast<const float4*>(crow);
+                v.x += o.x; v.y += o.y; v.z += o.z; v.w += o.w;
+              } else {
+                v.x += crow[0];
+                if (gn + 1 < g.n) v.y += crow[1];
+                if (gn + 2 < g.n) v.z += crow[2];
+                if (gn + 3 < g.n) v.w += crow[3];
+              }
+            }
+            v.x += bb.x; v.y += bb.y; v.z += bb.z; v.w += bb.w;
+            if (relu) {
+              v.x = fmaxf(v.x, 0.f); v.y = fmaxf(v.y, 0.f); v.z = fmaxf(v.z, 0.f); v.w = fmaxf(v.w, 0.f);
+            } else if (other) {
+              v.x = act_apply(v.x, g.act); v.y = act_apply(v.y, g.act);
+              v.z = act_apply(v.z, g.act); v.w = act_apply(v.w, g.act);
+            }
+            if (vec) *reinterpret_cast<float4*>(crow) = v;
+            else {
+              crow[0] = v.x;
+              if (gn + 1 < g.n) crow[1] = v.y;
+              if (gn + 2 < g.n) crow[2] = v.z;
+              if (gn + 3 < g.n) crow[3] = v.w;
+            }
+          }
+          __syncwarp();                    // the staging block is rewritten by the next column group
         }
       }
       if (nkb > 0) {      // hand the accumulator back to the MMA issuer of the pair
@@ -1562,7 +1549,7 @@ __global__ void __launch_bounds__(WsLayout<CIN>::kThreads, 1)
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
   __syncthreads();
   if constexpr (NCTA > 1) cluster_sync_all();      // no CTA leaves while its peer may still signal it
-  if (warp == WsLayout<CIN>::kMmaWarp) {
+  if (warp == WsLayout<GEN != 0>::kMmaWarp) {
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
     if constexpr (NCTA == 1)
       asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(TMEM_COLS) : "memory");
@@ -1576,11 +1563,12 @@ struct TmaMaps {
   bool ok;
 };
 
-template <int BN, int STAGES, int NCTA, bool TMA, bool CIN = false, bool FOLD = false>
+template <int BN, int STAGES, int NCTA, bool TMA, int GEN = 0, bool FOLD = false>
 static cudaError_t launch_ws_impl(const WsArgs& wa, const TmaMaps& tm, cudaStream_t st) {
-  constexpr size_t smem = (size_t)STAGES * (2 * kTM * 128 + 2 * (BN / NCTA) * 128) + 1024;
+  constexpr size_t smem = (size_t)STAGES * (2 * kTM * 128 + 2 * (BN / NCTA) * 128) + 1024 +
+                          (FOLD ? 0 : kWsEpilogueWarps * 4096);     // + the epilogue's transpose staging
   static_assert(smem + 256 <= 227 * 1024, "stage ring exceeds shared memory");
-  auto kern = gemm_planes_ws_kernel<BN, STAGES, NCTA, TMA, CIN, FOLD>;
+  auto kern = gemm_planes_ws_kernel<BN, STAGES, NCTA, TMA, GEN, FOLD>;
   cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) return e;
   const int64_t max_clusters = kNumSMs / NCTA;
@@ -1592,7 +1580,7 @@ static cudaError_t launch_ws_impl(const WsArgs& wa, const TmaMaps& tm, cudaStrea
   }
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = dim3((unsigned)(nclusters * NCTA));
-  cfg.blockDim = dim3(WsLayout<CIN>::kThreads);
+  cfg.blockDim = dim3(WsLayout<GEN != 0>::kThreads);
   cfg.dynamicSmemBytes = smem;
   cfg.stream = st;
   cudaLaunchAttribute attr[1];
@@ -1777,11 +1765,11 @@ static b2ctr_status_t gemm_planes(const b2ctr_gemm_t* g, void* workspace, size_t
             tma_map_2d(&tm.bl, b_lo, b_pitch, b_prows, b_pitch, 64, b_mn ? 64 : bnh);
     if (ncta == 2) {
       if (bn == 32) e = launch_ws<32, 5, 2>(wa, tm, st);
-      else if (bn == 64) e = launch_ws<64, 5, 2>(wa, tm, st);
+      else if (bn == 64) e = launch_ws<64, 4, 2>(wa, tm, st);
       else if (bn == 128) e = launch_ws<128, 4, 2>(wa, tm, st);
       else e = launch_ws<256, 3, 2>(wa, tm, st);
     } else {
-      if (bn == 32) e = launch_ws<32, 5, 1>(wa, tm, st);
+      if (bn == 32) e = launch_ws<32, 4, 1>(wa, tm, st);
       else if (bn == 64) e = launch_ws<64, 4, 1>(wa, tm, st);
       else if (bn == 128) e = launch_ws<128, 3, 1>(wa, tm, st);
       else e = launch_ws<256, 2, 1>(wa, tm, st);
@@ -1856,6 +1844,17 @@ static size_t gen_gemm_workspace_bytes(const GenSpec& sp, int mode, int64_t n, i
   return split_k > 1 ? (size_t)split_k * M * n * sizeof(float) + 256 : 0;
 }
 
+template <int GEN>
+static cudaError_t launch_gen(const WsArgs& wa, const TmaMaps& tm, int bn, int ncta, cudaStream_t st) {
+  if (ncta == 2) {
+    if (bn == 128) return launch_ws_impl<128, 4, 2, true, GEN>(wa, tm, st);
+    return launch_ws_impl<256, 3, 2, true, GEN>(wa, tm, st);
+  }
+  if (bn == 64) return launch_ws_impl<64, 4, 1, true, GEN>(wa, tm, st);
+  if (bn == 128) return launch_ws_impl<128, 3, 1, true, GEN>(wa, tm, st);
+  return launch_ws_impl<256, 2, 1, true, GEN>(wa, tm, st);
+}
+
 // mode 0: c[rows, n] = act(A B + bias), B = planes of a [kq, n] row-major matrix; mode 1: c[kq, n] = A^T dY,
 // dY given as the planes of a [rows, n] row-major matrix.
 static b2ctr_status_t gen_gemm(const GenSpec& sp, int mode, int64_t n, const void* planes, float* c, int64_t ldc,
@@ -1879,7 +1878,7 @@ static b2ctr_status_t gen_gemm(const GenSpec& sp, int mode, int64_t n, const voi
     // measured (profiles/README.md): the CIN generator is faster with all 256 threads on every stage (C3 8.02 vs
     // 8.32 ms), the (non-resident) attention generator with two groups alternating stages (C4 3.55 vs 3.59 ms)
     // (the attention generator keeps its keys in registers when a thread's e-range is fixed: 64 % E == 0, E >= 32)
-    pa.gen_groups = groups == 1 || groups == 2 ? groups : (sp.kind == 1 || (sp.h >= 32 && 64 % sp.h == 0) ? 1 : 2);
+    pa.gen_groups = sp.kind == 1 ? 1 : groups == 1 || groups == 2 ? groups : ((sp.h >= 32 && 64 % sp.h == 0) ? 1 : 2);
   }
   pa.b_mn = 1;      // both B operands are row-major matrices whose reduction dim is their row index
   pa.c = c; pa.bias = bias; pa.ws = (float*)workspace; pa.ldc = ldc;
@@ -1912,15 +1911,7 @@ static b2ctr_status_t gen_gemm(const GenSpec& sp, int mode, int64_t n, const voi
     return B2CTR_ERR_UNSUPPORTED;
   }
   tm.ah = tm.bh; tm.al = tm.bl;
-  cudaError_t e;
-  if (ncta == 2) {
-    if (bn == 128) e = launch_ws_impl<128, 4, 2, true, true>(wa, tm, st);
-    else e = launch_ws_impl<256, 3, 2, true, true>(wa, tm, st);
-  } else {
-    if (bn == 64) e = launch_ws_impl<64, 4, 1, true, true>(wa, tm, st);
-    else if (bn == 128) e = launch_ws_impl<128, 3, 1, true, true>(wa, tm, st);
-    else e = launch_ws_impl<256, 2, 1, true, true>(wa, tm, st);
-  }
+  const cudaError_t e = sp.kind == 1 ? launch_gen<1>(wa, tm, bn, ncta, st) : launch_gen<2>(wa, tm, bn, ncta, st);
   if (e != cudaSuccess) {
     set_error("%s: CUDA launch failed: %s", what, cudaGetErrorString(e));
     return B2CTR_ERR_CUDA;
@@ -1993,8 +1984,8 @@ b2ctr_status_t cin_fold(const b2ctr_cin_gemm_t* g, float* dt0, float* dxk, int64
     set_error("cin_fold: cuTensorMapEncodeTiled unavailable");
     return B2CTR_ERR_UNSUPPORTED;
   }
-  cudaError_t e = ncta == 2 ? launch_ws_impl<128, 4, 2, true, false, true>(wa, tm, st)
-                            : launch_ws_impl<128, 3, 1, true, false, true>(wa, tm, st);
+  cudaError_t e = ncta == 2 ? launch_ws_impl<128, 4, 2, true, 0, true>(wa, tm, st)
+                            : launch_ws_impl<128, 3, 1, true, 0, true>(wa, tm, st);
   if (e != cudaSuccess) {
     set_error("b2ctr_cin_fold: CUDA launch failed: %s", cudaGetErrorString(e));
     return B2CTR_ERR_CUDA;

@@ -1877,8 +1877,9 @@ static b2ctr_status_t gen_gemm(const GenSpec& sp, int mode, int64_t n, const voi
     if (groups < 0) { const char* ev = getenv("B2CTR_GEN_GROUPS"); groups = ev ? atoi(ev) : 0; }
     // measured (profiles/README.md): the CIN generator is faster with all 256 threads on every stage (C3 8.02 vs
     // 8.32 ms), the (non-resident) attention generator with two groups alternating stages (C4 3.55 vs 3.59 ms)
-    // (the attention generator keeps its keys in registers when a thread's e-range is fixed: 64 % E == 0, E >= 32)
-    pa.gen_groups = sp.kind == 1 ? 1 : groups == 1 || groups == 2 ? groups : ((sp.h >= 32 && 64 % sp.h == 0) ? 1 : 2);
+    // measured (C4, E = 64): the register-resident attention generator (B2CTR_GEN_GROUPS=1) is slower than the
+    // two-group one, 2.88 vs 2.61 ms per step
+    pa.gen_groups = sp.kind == 1 ? 1 : (groups == 1 ? 1 : 2);
   }
   pa.b_mn = 1;      // both B operands are row-major matrices whose reduction dim is their row index
   pa.c = c; pa.bias = bias; pa.ws = (float*)workspace; pa.ldc = ldc;

@@ -380,6 +380,8 @@ struct PlaneArgs {
   // FOLD epilogue (CIN backward): dT0 [rows, cin_ld0] and dXk [rows, fold_ldx], both accumulated with red.add
   float* fold_dt0; float* fold_dxk; int64_t fold_ldx;
   int gen_groups;     // generating producers: 2 = two groups of 128 threads alternate stages, 1 = all 256 share every stage
+  int debug;          // B2CTR_TC_DEBUG knock-outs (WRONG RESULTS; tools/gemm_sweep.py attributes the per-tile cost with them):
+                      // 1 = no global stores in the epilogue, 2 = no tcgen05.ld, 4 = no MMAs issued, 8 = no operand loads
 };
 
 // dst planes [rows_pad, k_pad] <- src(r, k) = p[r*sr + k*sk]; zero outside [rows, k).
@@ -1186,6 +1188,7 @@ __global__ void __launch_bounds__(WsLayout<GEN != 0>::kThreads, 1)
           const int s = it % STAGES;
           mbar_wait(&empty_bar[s], ((it / STAGES) & 1) ^ 1);
           uint64_t* bar = &full_bar[s];
+          if (g.debug & 8) { mbar_arrive(bar); continue; }
           mbar_expect_tx(bar, (uint32_t)STAGE);
           const uint32_t st = smem_u32(tiles + (size_t)s * STAGE);
           const int32_t k0 = (int32_t)(kbeg + (int64_t)kb * kTK);
@@ -1303,6 +1306,7 @@ __global__ void __launch_bounds__(WsLayout<GEN != 0>::kThreads, 1)
             const uint32_t a_hi = sa, a_lo = sa + A_PLANE, b_hi = sa + 2 * A_PLANE, b_lo = sa + 2 * A_PLANE + B_PLANE;
 #pragma unroll
             for (int ks = 0; ks < kTK / 16; ++ks) {
+              if (g.debug & 4) break;
               const uint64_t dah = umma_desc_any(a_hi, ks, g.a_mn), dal = umma_desc_any(a_lo, ks, g.a_mn);
               const uint64_t dbh = umma_desc_any(b_hi, ks, g.b_mn), dbl = umma_desc_any(b_lo, ks, g.b_mn);
               umma_f16_ws<NCTA>(tmem_d, dah, dbh, idesc, (kb | ks) ? 1u : 0u);
@@ -1448,7 +1452,7 @@ __global__ void __launch_bounds__(WsLayout<GEN != 0>::kThreads, 1)
           const int64_t gn0 = nt * BN + c0;
           if (gn0 >= g.n) break;           // warp-uniform
           uint32_t r[32];
-          if (nkb > 0) {
+          if (nkb > 0 && !(g.debug & 2)) {
             const uint32_t taddr = tmem_base + ((uint32_t)(sub * 32) << 16) + ab * BN + (uint32_t)c0;
             asm volatile(
                 "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
@@ -1465,7 +1469,7 @@ __global__ void __launch_bounds__(WsLayout<GEN != 0>::kThreads, 1)
 #pragma unroll
             for (int j = 0; j < 32; ++j) r[j] = 0u;
           }
-          if (row_base >= g.m) continue;   // warp-uniform: the whole 32-row block is padding
+          if (row_base >= g.m || (g.debug & 1)) continue;   // warp-uniform: the whole 32-row block is padding
 #pragma unroll
           for (int c = 0; c < 8; ++c)      // row `lane`, 16-byte chunk c -> physical chunk c ^ (lane & 7)
             *reinterpret_cast<uint4*>(stg + lane * 128 + ((c ^ (lane & 7)) << 4)) =
@@ -1556,6 +1560,12 @@ __global__ void __launch_bounds__(WsLayout<GEN != 0>::kThreads, 1)
     else
       asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(TMEM_COLS) : "memory");
   }
+}
+
+static int tc_debug() {
+  static int v = -1;
+  if (v < 0) { const char* e = getenv("B2CTR_TC_DEBUG"); v = e ? atoi(e) : 0; }
+  return v;
 }
 
 struct TmaMaps {
@@ -1745,7 +1755,7 @@ static b2ctr_status_t gemm_planes(const b2ctr_gemm_t* g, void* workspace, size_t
   pa.k_per_split = ceil_div(ceil_div(kp, splits), kTK) * kTK;
   pa.alpha = g->alpha; pa.act = g->act; pa.accumulate = g->accumulate; pa.splits = splits;
   pa.cin_on = 0; pa.cin_t0 = pa.cin_xk = nullptr; pa.cin_ld0 = pa.cin_ldk = pa.cin_rows = 0; pa.cin_m = pa.cin_h = pa.cin_hp = 0;
-  pa.fold_dt0 = pa.fold_dxk = nullptr; pa.fold_ldx = 0; pa.gen_groups = 0;
+  pa.fold_dt0 = pa.fold_dxk = nullptr; pa.fold_ldx = 0; pa.gen_groups = 0; pa.debug = tc_debug();
   cudaError_t e;
   const bool short_k = pa.k_per_split <= 4 * kTK;
   if (ws_kernel) {
@@ -1871,7 +1881,7 @@ static b2ctr_status_t gen_gemm(const GenSpec& sp, int mode, int64_t n, const voi
   pa.a_hi = pa.a_lo = nullptr; pa.a_pitch = 0;
   pa.cin_on = sp.kind; pa.cin_t0 = sp.p0; pa.cin_xk = sp.p1; pa.cin_ld0 = sp.ld0; pa.cin_ldk = sp.ld1;
   pa.cin_rows = sp.rows; pa.cin_m = sp.m; pa.cin_h = sp.h; pa.cin_hp = sp.hp;
-  pa.fold_dt0 = pa.fold_dxk = nullptr; pa.fold_ldx = 0;
+  pa.fold_dt0 = pa.fold_dxk = nullptr; pa.fold_ldx = 0; pa.debug = 0;
   {
     static int groups = -1;
     if (groups < 0) { const char* ev = getenv("B2CTR_GEN_GROUPS"); groups = ev ? atoi(ev) : 0; }
@@ -1969,7 +1979,7 @@ b2ctr_status_t cin_fold(const b2ctr_cin_gemm_t* g, float* dt0, float* dxk, int64
   pa.k_per_split = pa.k_pad; pa.alpha = 1.f; pa.act = 0; pa.accumulate = 0; pa.splits = 1;
   pa.cin_on = 0; pa.cin_t0 = g->t0; pa.cin_xk = g->xk; pa.cin_ld0 = g->ld0; pa.cin_ldk = g->ldk; pa.cin_rows = g->rows;
   pa.cin_m = g->m; pa.cin_h = g->h; pa.cin_hp = g->hp;
-  pa.fold_dt0 = dt0; pa.fold_dxk = dxk; pa.fold_ldx = ldx; pa.gen_groups = 0;
+  pa.fold_dt0 = dt0; pa.fold_dxk = dxk; pa.fold_ldx = ldx; pa.gen_groups = 0; pa.debug = 0;
   constexpr int bn = 128;
   const int ncta = g->rows > kTM ? 2 : 1;
   WsArgs wa;

@@ -762,6 +762,19 @@ __device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map
       "l"(map), "r"(c0), "r"(c1), "r"(smem_u32(bar))
       : "memory");
 }
+// CTA pair: the load issued by either CTA of the pair signals the LEADER's mbarrier (shared::cluster address `bar`),
+// so the MMA issuer waits on one barrier per stage and no warp has to relay "the peer's half has landed".
+__device__ __forceinline__ void tma_load_2d_pair(uint32_t dst, const CUtensorMap* map, int32_t c0, int32_t c1, uint32_t bar) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];" ::"r"(dst),
+      "l"(map), "r"(c0), "r"(c1), "r"(bar)
+      : "memory");
+}
+__device__ __forceinline__ uint32_t mapa_u32(uint32_t addr, uint32_t cta) {
+  uint32_t r;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(addr), "r"(cta));
+  return r;
+}
 __device__ __forceinline__ void tma_prefetch_desc(const CUtensorMap* map) {
   asm volatile("prefetch.tensormap [%0];" ::"l"(map) : "memory");
 }
@@ -1189,28 +1202,34 @@ __global__ void __launch_bounds__(WsLayout<GEN != 0>::kThreads, 1)
           mbar_wait(&empty_bar[s], ((it / STAGES) & 1) ^ 1);
           uint64_t* bar = &full_bar[s];
           if (g.debug & 8) { mbar_arrive(bar); continue; }
-          mbar_expect_tx(bar, (uint32_t)STAGE);
+          // CTA pair: both CTAs' loads complete on the LEADER's barrier, armed there with the bytes of both halves
+          if (NCTA == 1 || cta_rank == 0) mbar_expect_tx(bar, (uint32_t)(NCTA * STAGE));
+          const uint32_t lbar = NCTA == 1 ? smem_u32(bar) : mapa_u32(smem_u32(bar), 0);
+          auto load = [&](uint32_t dst, const CUtensorMap* map, int32_t c0, int32_t c1) {
+            if constexpr (NCTA == 1) tma_load_2d(dst, map, c0, c1, bar);
+            else tma_load_2d_pair(dst, map, c0, c1, lbar);
+          };
           const uint32_t st = smem_u32(tiles + (size_t)s * STAGE);
           const int32_t k0 = (int32_t)(kbeg + (int64_t)kb * kTK);
           if (g.a_mn) {        // [k, m] planes: one 64(m) x 64(k) box per 64-wide atom
 #pragma unroll
             for (int j = 0; j < kTM / 64; ++j) {
-              tma_load_2d(st + j * 8192, &tm_ah, m0 + 64 * j, k0, bar);
-              tma_load_2d(st + A_PLANE + j * 8192, &tm_al, m0 + 64 * j, k0, bar);
+              load(st + j * 8192, &tm_ah, m0 + 64 * j, k0);
+              load(st + A_PLANE + j * 8192, &tm_al, m0 + 64 * j, k0);
             }
           } else {             // [m, k] planes: one 64(k) x 128(m) box
-            tma_load_2d(st, &tm_ah, k0, m0, bar);
-            tma_load_2d(st + A_PLANE, &tm_al, k0, m0, bar);
+            load(st, &tm_ah, k0, m0);
+            load(st + A_PLANE, &tm_al, k0, m0);
           }
           if (g.b_mn) {
 #pragma unroll
             for (int j = 0; j < (BNH >= 64 ? BNH / 64 : 1); ++j) {
-              tma_load_2d(st + 2 * A_PLANE + j * 8192, &tm_bh, n0 + 64 * j, k0, bar);
-              tma_load_2d(st + 2 * A_PLANE + B_PLANE + j * 8192, &tm_bl, n0 + 64 * j, k0, bar);
+              load(st + 2 * A_PLANE + j * 8192, &tm_bh, n0 + 64 * j, k0);
+              load(st + 2 * A_PLANE + B_PLANE + j * 8192, &tm_bl, n0 + 64 * j, k0);
             }
           } else {
-            tma_load_2d(st + 2 * A_PLANE, &tm_bh, k0, n0, bar);
-            tma_load_2d(st + 2 * A_PLANE + B_PLANE, &tm_bl, k0, n0, bar);
+            load(st + 2 * A_PLANE, &tm_bh, k0, n0);
+            load(st + 2 * A_PLANE + B_PLANE, &tm_bl, k0, n0);
           }
         }
       }
@@ -1299,7 +1318,7 @@ __global__ void __launch_bounds__(WsLayout<GEN != 0>::kThreads, 1)
         for (int kb = 0; kb < nkb; ++kb, ++it) {
           const int s = it % STAGES;
           mbar_wait(&full_bar[s], (it / STAGES) & 1);
-          if constexpr (NCTA > 1) mbar_wait_cluster(&peer_full[s], (it / STAGES) & 1);
+          if constexpr (NCTA > 1 && !(TMA && GEN == 0)) mbar_wait_cluster(&peer_full[s], (it / STAGES) & 1);
           asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
           if (lane == 0) {
             const uint32_t sa = smem_u32(tiles + (size_t)s * STAGE);
@@ -1320,8 +1339,9 @@ __global__ void __launch_bounds__(WsLayout<GEN != 0>::kThreads, 1)
         }
         ++acc_it;
       }
-    } else {
-      // peer CTA: relay "my half of stage s has landed" to the leader, which issues the MMAs of the pair
+    } else if constexpr (!(TMA && GEN == 0)) {
+      // peer CTA (cp.async / generated operands): relay "my half of stage s has landed" to the leader, which issues
+      // the MMAs of the pair.  With TMA for both operands the peer's loads signal the leader's barrier themselves.
       uint32_t it = 0;
       for (int64_t tile = cluster_id; tile < w.ntiles; tile += nclusters) {
         int64_t mt, nt, kbeg;

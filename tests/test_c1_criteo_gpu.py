@@ -64,6 +64,11 @@ def test_deepfm_criteo_sample_training_matches_oracle(cuda):
     l2 = {n: (1e-5 if (n.startswith("tables/") or n == "linear_kernel") else 0.0) for n in leaves}
     m = {n: torch.zeros_like(t) for n, t in leaves.items()}
     v = {n: torch.zeros_like(t) for n, t in leaves.items()}
+    # before any training: logits-level parity at the north_star tolerance (1e-4) on the held-out rows
+    x_te_np = {n: np.asarray(x_te[n]) for n in names}
+    with torch.no_grad():
+        _, want0 = OM.deepfm(x_te_np, cols, cols, W)
+    assert H.rel_err(model.predict(x_te, batch_size=256), want0.numpy()) < 1e-4
     split = int(len(y_tr) * 0.8)                         # validation_split=0.2 takes the LAST 20 %
     xo = {n: np.asarray(x_tr[n])[:split] for n in names}
     yo = y_tr[:split].reshape(-1)
@@ -92,9 +97,10 @@ def test_deepfm_criteo_sample_training_matches_oracle(cuda):
     for a, b in zip(got, want_losses):
         assert abs(a - b) < 2e-3 * max(1.0, abs(b)), (got, want_losses)
     assert got[-1] < got[0]
-    # predictions on the held-out 40 rows after training: model vs oracle weights
+    # predictions on the held-out 40 rows after 6 dense-Adam steps (fp32 Adam amplifies last-bit differences of the
+    # gradients through 1/sqrt(v): the trajectories are compared at 2e-3, the untrained model above at 1e-4)
     pred = model.predict(x_te, batch_size=256)
-    _, want = OM.deepfm({n: np.asarray(x_te[n]) for n in names}, cols, cols, W)
+    _, want = OM.deepfm(x_te_np, cols, cols, W)
     assert pred.shape == (40, 1)
     assert H.rel_err(pred, want.detach().numpy()) < 2e-3
     from sklearn.metrics import log_loss, roc_auc_score

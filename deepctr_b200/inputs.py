@@ -447,15 +447,10 @@ class EmbeddingPlanner(object):
         import os
         mode = os.environ.get("B2CTR_SHARD_MODE", "auto")
         if mode == "auto":
-            # Peer transport maps every other rank's shards and reads / updates their rows in place.  Measured
-            # (DESIGN.md section 9): with 166 GB of shards per rank it runs at full rate on 2 GPUs (166 GB peer-mapped)
-            # but at ~50 GB/s on 8 GPUs (1.16 TB peer-mapped: random rows over that footprint miss the address-
-            # translation caches on every access).  Beyond half a terabyte of peer-mapped rows the owners gather
-            # locally and the rows travel as bulk NCCL all-to-all messages instead.
             shard_bytes = sum(int(np.prod(w_.shape_)) * 4 for w_ in
                               {id(s_.emb.embeddings): s_.emb.embeddings
                                for s_ in list(self.main[:self.fast_n]) + (list(self.lin) if lin_ok else [])}.values())
-            mode = "a2a" if shard_bytes * (ctx.world - 1) > (512 << 30) else "peer"
+            mode = parallel.choose_transport(shard_bytes, ctx.world)
         pow2 = ctx.world & (ctx.world - 1) == 0
         self.peer_mode = mode == "peer" and pow2 and ctx.backend == "nccl"
         self.peers = None            # built lazily (tables must be materialised on the device first)

@@ -84,6 +84,20 @@ def _contig_strides(shape):
     return tuple(reversed(out))
 
 
+PEER_MAPPED_LIMIT = 384 << 30
+
+
+def choose_transport(shard_bytes, world):
+    """'peer' or 'a2a' for row-sharded tables of `shard_bytes` per rank.
+
+    Peer transport maps every other rank's shards and reads / updates their rows in place over NVLink.  Measured
+     with 166 GB of shards per rank: full rate on 2 GPUs (166 GB peer-mapped per rank), ~50 GB/s
+    on 8 GPUs (1.16 TB peer-mapped: random rows over that footprint miss the address-translation caches on every
+    access), where the NCCL all-to-all transport - owners gather / update locally, rows travel as bulk messages - is
+    4.2x faster.  The switch-over sits between the two measured points."""
+    return "a2a" if shard_bytes * (world - 1) > PEER_MAPPED_LIMIT else "peer"
+
+
 def device_barrier(ctx, token):
     """Stream-ordered cross-rank barrier: a 4-byte all-reduce completes only when every rank has reached it
     on its stream (no host synchronisation)."""

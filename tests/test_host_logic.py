@@ -200,3 +200,14 @@ def test_dense_gemm_policy_helpers():
     assert not K.planes_fusable(65536, 1) and not K.planes_fusable(65537, 256) and not K.planes_fusable(256, 96)
     assert not K.planes_fusable(256, 2048)                # wider than one vectorised row group
     assert ops.GEMM_PRECISION == __import__("deepctr_b200._lib", fromlist=["x"]).GEMM_BF16X3
+
+
+def test_shard_transport_choice():
+    """row-sharded tables: peer mappings up to ~0.4 TB of peer-mapped rows, NCCL all-to-all beyond"""
+    from deepctr_b200 import parallel
+    c2 = 26 * 1000000 * 33 * 4                    # C2: 3.4 GB of tables in total
+    assert parallel.choose_transport(c2 // 8, 8) == "peer"
+    c5 = 26 * 12500000 * 129 * 4                  # C5: 167.7 GB per rank
+    assert parallel.choose_transport(c5, 2) == "peer"      # measured: full rate
+    assert parallel.choose_transport(c5, 8) == "a2a"       # measured: peer 17.6 ms, all-to-all 4.2 ms per step
+    assert parallel.choose_transport(c5, 1) == "peer"

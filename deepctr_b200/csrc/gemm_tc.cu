@@ -668,10 +668,16 @@ static cudaError_t launch_planes(const PlaneArgs& pa, cudaStream_t st) {
 // (96 KB per 64-deep k-block per SM, ~11 TB/s over 148 SMs).  A CTA pair computes a 256 x BN tile with
 // each CTA staging its own 128 rows of A and only HALF of the B tile (the pair's tensor cores read both
 // halves), i.e. 64 KB per k-block per SM at BN = 256 - which also leaves room for a 3-deep pipeline.
-//   warps 0-7  : epilogue (TMEM -> registers -> global); warp & 3 = TMEM sub-partition, warp >> 2 = column half
-//   warps 8-11 : producers (cp.async 16 B chunks into the SWIZZLE_128B stage layout)
-//   warp  12   : TMEM allocation; lane 0 of the LEADER CTA issues every tcgen05.mma of the pair
+//   warps 0-7  : epilogue (TMEM -> registers -> 32x32 transposition through a swizzled staging block -> global,
+//                128 contiguous bytes per row); warp & 3 = TMEM sub-partition, warp >> 2 = column half
+//   producers  : TMA (default): one elected thread arms the stage barrier and issues cp.async.bulk.tensor.2d loads
+//                of the four plane slices; in a CTA pair both CTAs' loads complete on the LEADER's barrier
+//                (.cta_group::2).  GEN = 1 / 2: eight warps GENERATE the A tile in shared memory (CIN outer product /
+//                DIN attention input) while B arrives by TMA.  B2CTR_TC_TMA=0: four warps of 16-byte cp.async.
+//   last warp  : TMEM allocation; lane 0 of the LEADER CTA issues every tcgen05.mma of the pair
 // TMEM holds two BN-column accumulators: the epilogue of tile i overlaps the main loop of tile i+1.
+// Measured anatomy of a k-block (tools/gemm_sweep.py, B2CTR_TC_DEBUG knock-outs): the stage round trip alone
+// (commit -> empty -> producer -> full -> issuer, nothing loaded or multiplied) costs 0.25 us per k-block over 4 stages.
 // Persistent: grid = min(#tiles, #SMs / NCTA) clusters; tile = cluster id + j * #clusters, N-tile fastest
 // (neighbouring clusters share the A rows through L2).
 // ================================================================================================

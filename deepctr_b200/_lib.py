@@ -122,6 +122,7 @@ SIGNATURES = {
     "b2ctr_fm_bwd": (_i32, [_vp, _i64, _i32, _i32, _vp, _vp, _i64, _i32, _i64, _vp]),
     "b2ctr_predict_loss": (_i32, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _i64, _i32, _vp]),
     "b2ctr_sgd_step": (_i32, [_vp, _vp, _f32, _f32, _i64, _vp]),
+    "b2ctr_sgd_step_multi": (_i32, [C.POINTER(C.c_void_p), C.POINTER(C.c_void_p), C.POINTER(C.c_int64), C.POINTER(C.c_float), _i32, _f32, _vp]),
     "b2ctr_adam_step": (_i32, [_vp, _vp, _vp, _vp, _f32, _f32, _f32, _f32, _f32, _i64, _i64, _vp]),
     "b2ctr_adam_step_dev": (_i32, [_vp, _vp, _vp, _vp, C.c_float, C.c_float, C.c_float, C.c_float, C.c_float, _vp,
                             _i64, _vp]),

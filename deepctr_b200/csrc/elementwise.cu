@@ -318,6 +318,24 @@ __global__ void sgd_kernel(float* w, const float* __restrict__ g, float lr, floa
        i += (int64_t)gridDim.x * blockDim.x)
     w[i] -= lr * (g[i] + 2.f * l2 * w[i]);
 }
+// every dense weight of a tower in ONE launch (blockIdx.y = tensor): the 9-14 per-weight launches of a step were
+// 3 us each for a few kB of work
+constexpr int kSgdMulti = 32;
+struct SgdMulti {
+  float* w[kSgdMulti];
+  const float* g[kSgdMulti];
+  int64_t n[kSgdMulti];
+  float l2[kSgdMulti];
+};
+__global__ void sgd_multi_kernel(const __grid_constant__ SgdMulti p, float lr) {
+  const int t = blockIdx.y;
+  float* w = p.w[t];
+  const float* __restrict__ g = p.g[t];
+  const int64_t n = p.n[t];
+  const float l2 = p.l2[t];
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
+    w[i] -= lr * (g[i] + 2.f * l2 * w[i]);
+}
 __global__ void adam_kernel(float* w, const float* __restrict__ g, float* m, float* v, float lr_t,
                             float b1, float b2, float eps, float l2, int64_t n) {
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n;
@@ -543,6 +561,26 @@ b2ctr_status_t b2ctr_sgd_step(float* w, const float* g, float lr, float l2, int6
   if (n <= 0) return B2CTR_OK;
   sgd_kernel<<<grid_for(n, 256, 8), 256, 0, ST>>>(w, g, lr, l2, n);
   B2_CHECK_LAUNCH("b2ctr_sgd_step");
+  return B2CTR_OK;
+}
+
+b2ctr_status_t b2ctr_sgd_step_multi(float* const* w, const float* const* g, const int64_t* n, const float* l2,
+                                    int32_t count, float lr, void* stream) {
+  B2_REQUIRE(w && g && n && l2 && count >= 0, "sgd_step_multi: NULL pointer");
+  for (int32_t base = 0; base < count; base += kSgdMulti) {
+    SgdMulti p;
+    const int32_t c = count - base < kSgdMulti ? count - base : kSgdMulti;
+    int64_t nmax = 0;
+    for (int32_t i = 0; i < c; ++i) {
+      B2_REQUIRE(w[base + i] && g[base + i] && n[base + i] >= 0, "sgd_step_multi: NULL tensor %d", base + i);
+      p.w[i] = w[base + i]; p.g[i] = g[base + i]; p.n[i] = n[base + i]; p.l2[i] = l2[base + i];
+      if (p.n[i] > nmax) nmax = p.n[i];
+    }
+    if (nmax == 0) continue;
+    dim3 grid((unsigned)grid_for(nmax, 256, 8), (unsigned)c);
+    sgd_multi_kernel<<<grid, 256, 0, ST>>>(p, lr);
+    B2_CHECK_LAUNCH("b2ctr_sgd_step_multi");
+  }
   return B2CTR_OK;
 }
 

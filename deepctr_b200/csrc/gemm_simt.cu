@@ -272,11 +272,12 @@ __global__ void __launch_bounds__(256) skinny_n_kernel(const GemmArgs g, int lpr
 // A stored [K, M] (wgrad of a skinny layer: C[m, n] = sum_k A[k, m] B(k, n), N <= 8, K = batch): a stream over
 // the rows of A; thread = (column m, one of 4 k-lanes), 8 independent row loads in flight, k-lanes meet in
 // shared memory.  One CTA per (64-column block, K slice); slices go through the split-K workspace.
-template <int N>
+template <int N, int COLS = 64>
 __global__ void __launch_bounds__(256) skinny_tn_kernel(const GemmArgs g) {
-  __shared__ float red[4][64][N];
-  const int col = threadIdx.x & 63, kl = threadIdx.x >> 6;
-  const int64_t m = (int64_t)blockIdx.x * 64 + col;
+  constexpr int KL = 256 / COLS;         // k-lanes: 4 for 64-column blocks, 16 for M <= 16 (the 13 dense features)
+  __shared__ float red[KL][COLS][N];
+  const int col = threadIdx.x % COLS, kl = threadIdx.x / COLS;
+  const int64_t m = (int64_t)blockIdx.x * COLS + col;
   const int64_t kbeg = (int64_t)blockIdx.z * g.k_per_split;
   const int64_t kend = kbeg + g.k_per_split < g.k ? kbeg + g.k_per_split : g.k;
   float acc[N];
@@ -284,17 +285,17 @@ __global__ void __launch_bounds__(256) skinny_tn_kernel(const GemmArgs g) {
   for (int n = 0; n < N; ++n) acc[n] = 0.f;
   if (m < g.m) {
     int64_t k = kbeg + kl;
-    for (; k + 28 < kend; k += 32) {
+    for (; k + 7 * KL < kend; k += 8 * KL) {
       float a[8];
 #pragma unroll
-      for (int u = 0; u < 8; ++u) a[u] = __ldg(g.a + (k + 4 * u) * g.sak + m);
+      for (int u = 0; u < 8; ++u) a[u] = __ldg(g.a + (k + KL * u) * g.sak + m);
 #pragma unroll
       for (int u = 0; u < 8; ++u)
 #pragma unroll
         for (int n = 0; n < N; ++n)
-          if (n < g.n) acc[n] = fmaf(a[u], __ldg(g.b + (k + 4 * u) * g.sbk + n * g.sbn), acc[n]);
+          if (n < g.n) acc[n] = fmaf(a[u], __ldg(g.b + (k + KL * u) * g.sbk + n * g.sbn), acc[n]);
     }
-    for (; k < kend; k += 4) {
+    for (; k < kend; k += KL) {
       const float a = __ldg(g.a + k * g.sak + m);
 #pragma unroll
       for (int n = 0; n < N; ++n)
@@ -308,7 +309,10 @@ __global__ void __launch_bounds__(256) skinny_tn_kernel(const GemmArgs g) {
 #pragma unroll
     for (int n = 0; n < N; ++n) {
       if (n < g.n) {
-        float v = g.alpha * (((red[0][col][n] + red[1][col][n]) + red[2][col][n]) + red[3][col][n]);
+        float v = 0.f;
+#pragma unroll
+        for (int l = 0; l < KL; ++l) v += red[l][col][n];        // ascending k-lane order
+        v *= g.alpha;
         if (g.splits > 1) {
           g.ws[((int64_t)blockIdx.z * g.m + m) * g.n + n] = v;
         } else {
@@ -462,6 +466,15 @@ b2ctr_status_t gemm_fp32(const b2ctr_gemm_t* g, void* workspace, size_t workspac
   if (!akc && g->n <= 8 && g->k >= 64) {
     // sak = lda (A stored [K, M]); the K slices of split-K launches land in the workspace as usual
     dim3 grid((unsigned)ceil_div(g->m, 64), 1, (unsigned)ga.splits);
+    if (g->m <= 16 && g->n <= 1) {         // a handful of columns (the dense features' [13, 1] kernel): 16 k-lanes
+      skinny_tn_kernel<1, 16><<<grid, 256, 0, st>>>(ga);
+      B2_CHECK_LAUNCH("b2ctr_gemm(fp32 skinny-TN)");
+      if (ga.splits > 1) {
+        launch_splitk_reduce(ga, st);
+        B2_CHECK_LAUNCH("b2ctr_gemm(splitk_reduce)");
+      }
+      return B2CTR_OK;
+    }
     const bool v4 = g->m % 4 == 0 && ga.sak % 4 == 0 && (reinterpret_cast<uintptr_t>(ga.a) & 15) == 0;
     if (v4 && g->n <= 1) skinny_tn_vec4_kernel<1><<<grid, 256, 0, st>>>(ga);
     else if (v4 && g->n <= 2) skinny_tn_vec4_kernel<2><<<grid, 256, 0, st>>>(ga);

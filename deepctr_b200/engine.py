@@ -793,6 +793,20 @@ class Optimizer(object):
                 self.step_dev.copy_(torch.tensor([self.iterations - 1], dtype=torch.int64))
             K.counter_add(self.step_dev, 1)
 
+    def apply_all(self, ws):
+        """One optimizer step for a list of weights (SGD: a single multi-tensor launch)."""
+        if self.name == "sgd":
+            live = [w for w in ws if w.grad is not None]
+            gs = [w.grad if w.grad.is_contiguous() else w.grad.contiguous() for w in live]
+            if any(g.numel() != w.data.numel() for g, w in zip(gs, live)):
+                raise ValueError("gradient / weight size mismatch")
+            K.sgd_step_multi([w.data for w in live], gs, self.lr, [w.l2 for w in live])
+            for w in live:
+                w.grad = None
+            return
+        for w in ws:
+            self.apply(w)
+
     def apply(self, w):
         g = w.grad
         if g is None:
@@ -1223,8 +1237,7 @@ class Model(object):
                                                     src.numel(), dst_off=off),
                     lambda flat, f: K.add_n([flat], scales=[f], out=flat))
             self.optimizer.begin_step()
-            for w in dense:
-                self.optimizer.apply(w)
+            self.optimizer.apply_all(dense)
         return loss_sum, pred, lt.shape[0]
 
     def train_step(self, x, y):

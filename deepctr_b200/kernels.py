@@ -393,6 +393,19 @@ def sgd_step(w, g, lr, l2=0.0):
     L.check(L.lib().b2ctr_sgd_step(ptr(w), ptr(g), lr, l2, w.numel(), stream()), "sgd_step")
 
 
+def sgd_step_multi(ws, gs, lr, l2s):
+    """w -= lr * (g + 2 l2 w) for a list of tensors in one launch."""
+    n = len(ws)
+    if n == 0:
+        return
+    _require_cuda(*ws)
+    _require_cuda(*gs)
+    wp, gp = (C.c_void_p * n)(*[ptr(t) for t in ws]), (C.c_void_p * n)(*[ptr(t) for t in gs])
+    nn = (C.c_int64 * n)(*[t.numel() for t in ws])
+    ll = (C.c_float * n)(*[float(v) for v in l2s])
+    L.check(L.lib().b2ctr_sgd_step_multi(wp, gp, nn, ll, n, lr, stream()), "sgd_step_multi")
+
+
 def adam_step(w, g, m, v, lr, step, beta1=0.9, beta2=0.999, eps=1e-7, l2=0.0):
     _require_cuda(w, g, m, v)
     L.check(L.lib().b2ctr_adam_step(ptr(w), ptr(g), ptr(m), ptr(v), lr, beta1, beta2, eps, l2, step,
@@ -467,7 +480,7 @@ def profile_summary():
 
 for _n in ("embed_update_sorted", "split_planes", "embed_gather_fwd", "embed_scatter_add", "embed_gather_uniform_fwd", "embed_scatter_uniform_bwd",
            "hash64", "gemm", "bias_act_bwd", "act_fwd", "add_n", "axpy", "fill", "copy2d", "rowsum", "fm_fwd",
-           "fm_bwd", "predict_loss", "sgd_step", "adam_step", "adagrad_step", "mask_nonzero_and",
+           "fm_bwd", "predict_loss", "sgd_step", "sgd_step_multi", "adam_step", "adagrad_step", "mask_nonzero_and",
            "mask_from_len"):
     globals()[_n] = _timed(globals()[_n])
 

@@ -327,6 +327,10 @@ B2CTR_API b2ctr_status_t b2ctr_predict_loss(const float* logit, const float* bia
 
 B2CTR_API b2ctr_status_t b2ctr_sgd_step(float* w, const float* g, float lr, float l2, int64_t n,
                                        void* stream);
+/* The same update for `count` tensors in one launch (host arrays of device pointers / sizes / l2 factors):
+ * w[t][i] -= lr * (g[t][i] + 2 * l2[t] * w[t][i]).  A tower's 9-14 dense weights are a few kB each. */
+B2CTR_API b2ctr_status_t b2ctr_sgd_step_multi(float* const* w, const float* const* g, const int64_t* n,
+                                              const float* l2, int32_t count, float lr, void* stream);
 /* Keras Adam (lr 1e-3, b1 .9, b2 .999, eps 1e-7): step counts from 1 */
 B2CTR_API b2ctr_status_t b2ctr_adam_step(float* w, const float* g, float* m, float* v, float lr,
                                         float beta1, float beta2, float eps, float l2,

@@ -197,6 +197,19 @@ def test_optimizers(cuda):
     w = w0.to(cuda)
     K.sgd_step(w, g.to(cuda), 0.1, 0.01)
     torch.testing.assert_close(w.cpu(), w0 - 0.1 * (g + 0.02 * w0), rtol=1e-6, atol=1e-6)
+    # the multi-tensor form (one launch for all the dense weights of a tower): bit-identical to the per-tensor kernel
+    sizes = [1, 7, 256, 5003, 40000] * 8                       # 40 tensors: two launches of <= 32
+    ws0 = [_r(rng, k) for k in sizes]
+    gs = [_r(rng, k) for k in sizes]
+    l2s = [0.0 if i % 2 else 0.01 for i in range(len(sizes))]
+    one = [t.to(cuda) for t in ws0]
+    many = [t.to(cuda) for t in ws0]
+    gd = [t.to(cuda) for t in gs]
+    for t, gg, l2 in zip(one, gd, l2s):
+        K.sgd_step(t, gg, 0.1, l2)
+    K.sgd_step_multi(many, gd, 0.1, l2s)
+    for a, b in zip(one, many):
+        assert torch.equal(a, b)
     # Adam: 3 steps vs torch.optim.Adam(eps=1e-7) - Keras places eps outside the bias correction
     wt = w0.clone().double()
     m = torch.zeros(n).double()
